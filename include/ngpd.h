@@ -1,0 +1,174 @@
+/* libngpd -- C ABI of the B200-native normal-guided point-cloud denoising hot path.
+ *
+ * The reference (Ruubje/Normal-Guided-Pointcloud-Denoiser, Pointcloud/Modules) has no FFI of its own:
+ * its seam is a Python object API that calls SciPy / torch-CPU / torch_scatter.  Each entry point below
+ * replaces one of those calls; the reference line it stands in for is cited next to it.  The Python
+ * mirror of the reference classes (package directory `normal-guided-pointcloud-denoiser_b200/`) binds
+ * these symbols with ctypes; INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter name ends in `_host`;
+ *   - positions / normals are fp32, row-major [n,3]; neighbour tables are int32, row-major [m,k];
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); calls are asynchronous on that
+ *     stream unless stated otherwise;
+ *   - return value 0 = ok, <0 = error, message in ngpd_last_error() (thread-local);
+ *   - no entry point falls back to the CPU: without a CUDA device every compute call fails.
+ */
+#ifndef NGPD_H
+#define NGPD_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ngpd_grid ngpd_grid_t;       /* frozen spatial index ("tree") */
+typedef struct ngpd_session ngpd_session_t; /* fused, tree-order denoising state */
+
+typedef struct ngpd_grid_info {
+    int64_t n;
+    double cell_size;
+    int32_t dims[3];
+    int32_t bricks;
+    int64_t occupied_cells;
+    int64_t bytes;
+    float bbox[6];
+    int32_t rebuilds;
+} ngpd_grid_info_t;
+
+const char* ngpd_last_error(void);
+int ngpd_version(void);
+
+/* ---- spatial index: replaces scipy.spatial.KDTree(graph.pos.cpu()), Selector.py:141 ---------------
+ * Copies the n points (the "construction-time positions"; later edits of `pos` do not affect the index,
+ * exactly like the SciPy tree).  cell_size <= 0 chooses the cell from the data so that an occupied cell
+ * holds about 0.4*k_hint points.  Synchronises `stream`. */
+int ngpd_grid_create(const float* pos, int64_t n, float cell_size, int k_hint, void* stream, ngpd_grid_t** out);
+int ngpd_grid_destroy(ngpd_grid_t* grid);
+int ngpd_grid_info(const ngpd_grid_t* grid, ngpd_grid_info_t* out);
+/* perm_out[s] = original index of the s-th point in tree (Morton) order */
+int ngpd_grid_order(const ngpd_grid_t* grid, int32_t* perm_out, void* stream);
+
+/* ---- k nearest neighbours: replaces KDTree.query(pos, k), Selector.py:243; torch_cluster.knn_graph,
+ * GraphBuilder.py:63 (NGPD_KNN_SKIP_SELF); torch_geometric.nn.pool.knn(x, y, 1), Utils.py:260-261.
+ * Rows ascend by (fp64 squared distance of the fp32 coordinates, tree index); slots beyond the tree size
+ * hold n, as SciPy does.  d2_out (nullable) receives the fp64 squared distances rounded to fp32. */
+#define NGPD_KNN_SKIP_SELF 1        /* query i IS tree point i: leave it out of its own row */
+#define NGPD_KNN_QUERY_IS_TREE 2    /* query i is the (possibly moved) tree point i: visit queries in tree order */
+#define NGPD_KNN_COHERENT 4         /* queries are already in a spatially coherent order: skip the ordering pass */
+int ngpd_knn(const ngpd_grid_t* grid, const float* query, int64_t m, int k, int flags,
+             int32_t* idx_out, float* d2_out, void* stream);
+
+/* nearest tree point only, for the metrics of Utils.py:253-295.  d2_out[m] = fp32 squared distance
+ * recomputed from the fp32 coordinates as the reference does; idx_out nullable. */
+int ngpd_nn_sqdist(const ngpd_grid_t* grid, const float* query, int64_t m, int flags,
+                   float* d2_out, int32_t* idx_out, void* stream);
+
+/* ---- neighbourhood kernels.  Row r describes centre point `rows ? rows[r] : r` with neighbours
+ * idx[offsets ? offsets[r] .. offsets[r+1] : r*k .. r*k+k) (CSR when offsets != NULL). -------------------- */
+
+/* GraphBuilder.getPVTDecompositionWithKNN, GraphBuilder.py:99-111: covariance of the neighbours about their
+ * mean, LAPACK-order eigen-decomposition; normals_out = eigenvector of the smallest eigenvalue. */
+int ngpd_pca_normals(const float* pos, const int32_t* idx, const int32_t* offsets, int64_t m, int k,
+                     float* normals_out, float* eigval_out /*nullable [m,3]*/, void* stream);
+
+/* Decompositionor.getBetterFilteredNVT, Decompositionor.py:278-300.  x_thresh = largest fp32 x with
+ * acos(x) > rho.  Outputs: eigval [m,3] ascending, eigvec [m,3,3] (columns), optional tensor [m,3,3]
+ * and weight count sumw [m]. */
+int ngpd_nvt(const float* pos, const float* nrm, const int32_t* idx, const int32_t* offsets, const int32_t* rows,
+             int64_t m, int k, float x_thresh, float* eigval_out, float* eigvec_out,
+             float* tensor_out /*nullable*/, int32_t* sumw_out /*nullable*/, void* stream);
+
+/* torch.linalg.eigh on a stack of symmetric 3x3 fp32 tensors (lower triangle read), LAPACK ssyevd order
+ * of operations and sign convention (Decompositionor.py:300). */
+int ngpd_eigh3(const float* tensors /*[m,3,3]*/, int64_t m, float* eigval_out, float* eigvec_out, void* stream);
+
+/* Decomposition.getVUSmoothedNormals, Decompositionor.py:92-106 */
+int ngpd_smooth_normals(const float* eigval, const float* eigvec, const float* nrm, int64_t m, float tau, float damp,
+                        float* out, void* stream);
+
+/* Decomposition.getClasses, Decompositionor.py:65-69; features_out nullable [m,3] = planarity, linearity, sphericity */
+int ngpd_classify(const float* eigval, int64_t m, float scale, uint8_t* labels_out, float* features_out, void* stream);
+
+/* flat_step's cloud-wide scalars, Denoiser.py:106-107: centre = mean of all gathered neighbours, delta = max
+ * distance of a gathered neighbour from it.  out4 = {cx, cy, cz, delta} (device). */
+int ngpd_center_delta(const float* pos, const int32_t* idx, int64_t total_neighbours, float* out4, void* stream);
+
+/* Denoiser.{flat,edge,feature,corner}_step, Denoiser.py:26-219.  pos_out [m,3] = new position of each row's
+ * centre.  edge_vec [n,3] only for NGPD_STEP_EDGE; center_delta (device, from ngpd_center_delta) only for FLAT. */
+#define NGPD_STEP_FLAT 0
+#define NGPD_STEP_EDGE 1
+#define NGPD_STEP_FEATURE 2
+#define NGPD_STEP_CORNER 3
+int ngpd_update(int kind, const float* pos, const float* nrm, const float* edge_vec, const int32_t* idx,
+                const int32_t* offsets, const int32_t* rows, int64_t m, int k, float alpha, float dmax,
+                const float* center_delta, float* pos_out, void* stream);
+
+/* sum of |pos[idx] - pos[row]| over all edges (TorchUtils.averageEdgeLength, Utils.py:298): out2 = {sum, count} fp64 */
+int ngpd_edge_length_sum(const float* pos, const int32_t* idx, const int32_t* rows, int64_t m, int k, double* out2, void* stream);
+
+/* ---- fused session: Processor.denoise / denoiseUntilMinimumError bodies (Processor.py:124-139,158-176)
+ * on tree-ordered float4 state.  The index is frozen on `tree_pos` (what Processor.__init__ saw); pos/nrm are
+ * the current state in ORIGINAL point order. */
+typedef struct ngpd_step_params {
+    int32_t k_feature;       /* 16 */
+    int32_t k_update;        /* 8  */
+    float x_thresh;          /* acos threshold for rho */
+    float tau, damp, scale;  /* .3, 3, .2 */
+    int32_t strategy[3];     /* NGPD_STEP_* per label; -1 = leave the class alone */
+    float alpha[3];
+    float dmax;
+} ngpd_step_params_t;
+
+int ngpd_session_create(const float* tree_pos, int64_t n, int k_hint, void* stream, ngpd_session_t** out);
+int ngpd_session_destroy(ngpd_session_t* s);
+int ngpd_session_set_state(ngpd_session_t* s, const float* pos, const float* nrm, void* stream);
+int ngpd_session_get_state(ngpd_session_t* s, float* pos_out, float* nrm_out, uint8_t* labels_out, void* stream);
+/* one iteration: kNN(k_feature) -> NVT -> smooth -> NVT -> classify -> class-sequential update; normals <- smoothed */
+int ngpd_session_step(ngpd_session_t* s, const ngpd_step_params_t* p, void* stream);
+/* k-NN edge lengths of the current positions incl. the zero self edge (Processor.py:120):
+ * out_host = {sum of lengths, edge count}; synchronises */
+int ngpd_session_mean_edge_length(ngpd_session_t* s, int k, double* out_host, void* stream);
+/* number of kernels the last ngpd_session_step launched */
+int ngpd_session_launch_count(const ngpd_session_t* s);
+/* tree-order views for tests/benchmarks: perm (sorted -> original) */
+int ngpd_session_order(const ngpd_session_t* s, int32_t* perm_out, void* stream);
+
+/* The step split into its dependency phases, so that a multi-GPU driver can refresh halo rows in between
+ * (ngpd_session_step is exactly: features 0, features 1, then per class [flat scalars 0, 1] + update, commit).
+ *   phase_features part 0: kNN(k_feature) + NVT on the current normals + smoothing  -> smoothed normals
+ *                  part 1: NVT on the smoothed normals -> labels + crease directions
+ *   phase_flat_scalars (only for a class whose strategy is NGPD_STEP_FLAT, Denoiser.py:106-107)
+ *                  part 0: {sum x, sum y, sum z, count} of the class' gathered neighbours -> buffer 3 (4 doubles)
+ *                  part 1: centre = sums/count, then max distance from it -> buffer 4 (4 floats: centre, delta)
+ *                  a multi-GPU driver all-reduces buffer 3 (sum) between the parts and buffer 4[3] (max) after
+ *   phase_update: class `key` moves, everything else is copied into the other position buffer
+ *   phase_commit_normals: graph.n = f_n (Processor.py:139) */
+int ngpd_session_phase_features(ngpd_session_t* s, const ngpd_step_params_t* p, int part, void* stream);
+int ngpd_session_phase_flat_scalars(ngpd_session_t* s, const ngpd_step_params_t* p, int key, int part, void* stream);
+int ngpd_session_phase_update(ngpd_session_t* s, const ngpd_step_params_t* p, int key, void* stream);
+int ngpd_session_phase_commit_normals(ngpd_session_t* s);
+/* Morton-slab partitioning: owned[s] != 0 marks the tree-order rows this rank computes; the rest are halo copies
+ * (read-only for this rank).  NULL clears the mask. */
+int ngpd_session_set_owned(ngpd_session_t* s, const uint8_t* owned_tree_order, void* stream);
+/* device views of session state in tree order: 0 positions (float4), 1 normals (float4), 2 smoothed normals
+ * (float4), 3 flat-step accumulators (4 doubles), 4 centre+delta (4 floats), 5 labels (u8), 6 neighbour table */
+void* ngpd_session_buffer(ngpd_session_t* s, int which);
+/* halo traffic: gather / scatter float4 rows of buffer `which` (0..2) listed by tree position */
+int ngpd_session_export_rows(ngpd_session_t* s, int which, const int32_t* rows, int64_t m, float* out4, void* stream);
+int ngpd_session_import_rows(ngpd_session_t* s, int which, const int32_t* rows, int64_t m, const float* in4, void* stream);
+
+/* End-to-end entry points with HOST buffers (the path the e2e measurement times): copy this step's positions and
+ * normals in, run `iterations` steps, copy positions / normals / labels back.  Synchronous. */
+int ngpd_session_run_host(ngpd_session_t* s, const ngpd_step_params_t* p, int iterations, const float* pos_host,
+                          const float* nrm_host, float* pos_out_host, float* nrm_out_host, uint8_t* labels_out_host,
+                          void* stream);
+int ngpd_denoise_host(const float* tree_pos_host, const float* pos_host, const float* nrm_host, int64_t n,
+                      const ngpd_step_params_t* p, int iterations, float* pos_out_host, float* nrm_out_host,
+                      uint8_t* labels_out_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NGPD_H */

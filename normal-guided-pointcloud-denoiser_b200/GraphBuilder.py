@@ -1,0 +1,136 @@
+"""Graph construction, PCA normals and normal orientation with the interface of the reference's
+Pointcloud/Modules/GraphBuilder.py (:40-209)."""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from .Object import Pointcloud
+from .Utils import GeneralUtils, TorchUtils
+
+
+class Graph:
+    """Attribute bag standing in for torch_geometric.data.Data: pos, n, edge_index, edge_attr, gt, gt_n."""
+
+    def __init__(self, **kw):
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+    @property
+    def num_nodes(self) -> int:
+        return self.pos.size(0)
+
+    @property
+    def num_edges(self) -> int:
+        return self.edge_index.size(1)
+
+
+class GraphBuilder:
+    def __init__(self, pointcloud: Pointcloud):
+        GeneralUtils.validateAttributes(pointcloud, ["v"])
+        _lib.require_cuda()
+        if not pointcloud.v.is_cuda:
+            pointcloud.v = pointcloud.v.cuda()
+            if pointcloud.n is not None:
+                pointcloud.n = pointcloud.n.cuda()
+        self.device = pointcloud.v.device
+        self.pointcloud = pointcloud
+        self.graph = Graph(pos=pointcloud.v)
+        if pointcloud.hasNormals():
+            self.graph.n = pointcloud.n
+
+    def getKNNEdgeIndex(self, k: int = 12) -> torch.Tensor:
+        """kNN graph of the CURRENT positions without self loops, row 0 = centre, row 1 = neighbour, grouped by
+        centre, neighbours ascending by distance (torch_cluster.knn_graph(..., flow="target_to_source"), :60-63)."""
+        g = self.graph
+        GeneralUtils.validateAttributes(g, ["pos"])
+        pos = _lib.dev(g.pos, torch.float32, "graph.pos")
+        table = _lib.Grid(pos, k_hint=k).knn(pos, k, _lib.KNN_SKIP_SELF | _lib.KNN_QUERY_IS_TREE)
+        centre = torch.arange(pos.size(0), device=pos.device).repeat_interleave(k)
+        return torch.stack([centre, table.reshape(-1).long()])
+
+    def getPVTDecompositionWithKNN(self, edge_index: torch.Tensor) -> torch.Tensor:
+        """Eigenvectors (columns, ascending eigenvalue) of each point's neighbour covariance (:99-111)."""
+        w, vec = self._pca(edge_index)
+        return vec
+
+    def _pca(self, edge_index: torch.Tensor):
+        g = self.graph
+        GeneralUtils.validateAttributes(g, ["pos"])
+        k = int(TorchUtils.validateKNNEdgeIndex(edge_index))
+        pos = _lib.dev(g.pos, torch.float32, "graph.pos")
+        n = pos.size(0)
+        table = edge_index[1].view(-1, k).to(torch.int32).contiguous()
+        # full decomposition through the voting-tensor entry point is not needed: the normal kernel returns the
+        # smallest eigenvector; for the (rarely used) full basis run the generic eigen kernel on the covariances
+        normals = torch.empty((n, 3), dtype=torch.float32, device=pos.device)
+        eigval = torch.empty((n, 3), dtype=torch.float32, device=pos.device)
+        _lib.check(_lib.load().ngpd_pca_normals(_lib.ptr(pos), _lib.ptr(table), None, n, k, _lib.ptr(normals), _lib.ptr(eigval),
+                                                _lib.stream()), "ngpd_pca_normals")
+        self._last_normals = normals
+        vj = pos[table.long()]
+        d = vj - vj.mean(dim=1, keepdim=True)
+        cov = torch.einsum("nki,nkj->nij", d, d).contiguous()
+        vec = torch.empty((n, 3, 3), dtype=torch.float32, device=pos.device)
+        _lib.check(_lib.load().ngpd_eigh3(_lib.ptr(cov), n, _lib.ptr(eigval), _lib.ptr(vec), _lib.stream()), "ngpd_eigh3")
+        return eigval, vec
+
+    def setPVTNormals(self, edge_index: torch.Tensor) -> None:
+        g = self.graph
+        k = int(TorchUtils.validateKNNEdgeIndex(edge_index))
+        pos = _lib.dev(g.pos, torch.float32, "graph.pos")
+        n = pos.size(0)
+        table = edge_index[1].view(-1, k).to(torch.int32).contiguous()
+        normals = torch.empty((n, 3), dtype=torch.float32, device=pos.device)
+        _lib.check(_lib.load().ngpd_pca_normals(_lib.ptr(pos), _lib.ptr(table), None, n, k, _lib.ptr(normals), None, _lib.stream()),
+                   "ngpd_pca_normals")
+        g.n = normals
+
+    def setAndFlipNormals(self, flip: bool = True) -> None:
+        g = self.graph
+        GeneralUtils.validateAttributes(g, ["edge_index"])
+        self.setPVTNormals(g.edge_index)
+        if flip:
+            self.flipNormals()
+
+    # ---- orientation (:129-209).  Preprocessing, runs once; host-side for now (SURVEY.md 8f rank 2 is the
+    # GPU version): edge cost 1-|ni.nj|, minimum spanning tree, propagate from the top-most point flipping a
+    # child when n_parent.n_child < cos(7pi/12).
+    def calculateEdgeCost(self) -> None:
+        g = self.graph
+        GeneralUtils.validateAttributes(g, ["edge_index", "n"])
+        nn = g.n[g.edge_index]
+        g.edge_attr = 1 - (nn[0] * nn[1]).sum(dim=-1).abs_()
+
+    def flipNormals(self) -> None:
+        from scipy.sparse import coo_matrix
+        from scipy.sparse.csgraph import breadth_first_order, minimum_spanning_tree
+
+        self.calculateEdgeCost()
+        g = self.graph
+        n = g.num_nodes
+        ei = g.edge_index.cpu().numpy()
+        # csgraph treats explicit zeros as missing edges: shift the costs into (0, 2]
+        cost = g.edge_attr.double().cpu().numpy() + 1e-9
+        lo, hi = np.minimum(ei[0], ei[1]), np.maximum(ei[0], ei[1])
+        order = np.lexsort((cost, hi, lo))
+        lo, hi, cost = lo[order], hi[order], cost[order]
+        first = np.ones(len(lo), dtype=bool)
+        first[1:] = (lo[1:] != lo[:-1]) | (hi[1:] != hi[:-1])
+        mst = minimum_spanning_tree(coo_matrix((cost[first], (lo[first], hi[first])), shape=(n, n)).tocsr())
+        mst = (mst + mst.T).tocsr()
+        nrm = g.n.detach().cpu().numpy().copy()
+        pos = g.pos.detach().cpu().numpy()
+        thr = math.cos(7.0 / 12.0 * math.pi)
+        root = int(np.argmax(pos[:, 2]))
+        if nrm[root, 2] < 0:
+            nrm[root] *= -1
+        visit, parent = breadth_first_order(mst, root, directed=False, return_predecessors=True)
+        for v in visit[1:]:
+            p = parent[v]
+            if float((nrm[p] * nrm[v]).sum(dtype=np.float32)) < thr:
+                nrm[v] *= -1
+        g.n = torch.from_numpy(nrm).to(g.pos.device)

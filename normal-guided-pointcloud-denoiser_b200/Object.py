@@ -1,0 +1,100 @@
+"""`Pointcloud` container and OBJ I/O with the interface of the reference's Pointcloud/Modules/Object.py
+(:43-162).  The OBJ reader is self-contained (the reference goes through libigl)."""
+from __future__ import annotations
+
+from pathlib import Path
+
+import numpy as np
+import torch
+
+
+def _default_device():
+    return "cuda" if torch.cuda.is_available() else "cpu"
+
+
+def read_obj(file_path: str):
+    """v [N,3] f64, vn [M,3] f64, face vertex ids [F,3] i64, face normal ids [Fn,3] i64 (0-based)."""
+    v, vn, fv, fn = [], [], [], []
+    with open(file_path, "r") as fh:
+        for line in fh:
+            if line.startswith("v "):
+                v.append(line.split()[1:4])
+            elif line.startswith("vn "):
+                vn.append(line.split()[1:4])
+            elif line.startswith("f "):
+                toks = line.split()[1:]
+                ids = [t.split("/") for t in toks]
+                # fan-triangulate polygons
+                for a in range(1, len(ids) - 1):
+                    tri = (ids[0], ids[a], ids[a + 1])
+                    fv.append([int(t[0]) - 1 for t in tri])
+                    if all(len(t) == 3 and t[2] != "" for t in tri):
+                        fn.append([int(t[2]) - 1 for t in tri])
+    arr = lambda x, dt: np.asarray(x, dtype=dt).reshape(-1, 3)
+    return arr(v, np.float64), arr(vn, np.float64), arr(fv, np.int64), arr(fn, np.int64)
+
+
+class Pointcloud:
+    def __init__(self, v: torch.Tensor, n: torch.Tensor = None) -> None:
+        assert v.is_floating_point()
+        assert v.dim() == 2
+        assert v.size(1) == 3
+        if n is not None:
+            assert n.is_floating_point()
+            assert n.dim() == 2
+            assert n.size(1) == 3
+            assert v.size(0) == n.size(0)
+        self.v = v
+        self.n = n
+        self.file_path = None
+
+    def hasNormals(self) -> bool:
+        return self.n is not None
+
+    def hasFilePath(self) -> bool:
+        return self.file_path is not None
+
+    def saveObj(self, file_path: str) -> None:
+        """Object.py:58-69: `v x y z` lines then `vn` lines; refuses to overwrite (mode "x")."""
+        with open(file_path, "x") as f:
+            f.write("# File made by Ruben Band\n")
+            for row in self.v.detach().cpu().tolist():
+                f.write("v " + " ".join(str(x) for x in row) + "\n")
+            if self.n is not None:
+                for row in self.n.detach().cpu().tolist():
+                    f.write("vn " + " ".join(str(x) for x in row) + "\n")
+        self.file_path = file_path
+
+    @classmethod
+    def loadObj(cls, file_path: str, device=None) -> "Pointcloud":
+        """Object.py:72-89.  Vertex normals are taken from `vn` records: accumulated over faces when the faces
+        reference them, used directly when there is one per vertex, otherwise the cloud has no normals."""
+        path = Path(file_path)
+        assert path.is_file()
+        assert path.suffix == ".obj"
+        device = device if device is not None else _default_device()
+        v, vn, fv, fn = read_obj(file_path)
+        vt = torch.tensor(v, dtype=torch.float, device=device)
+        if len(vn) > 0 and len(fn) > 0:
+            nt = torch.tensor(vn, dtype=torch.float, device=device)
+            acc = torch.zeros_like(vt)
+            acc.index_add_(0, torch.tensor(fv, device=device).view(-1), nt[torch.tensor(fn, device=device)].view(-1, 3))
+            pc = cls(vt, torch.nn.functional.normalize(acc, dim=-1))
+        elif len(vn) > 0 and len(vn) == len(v):
+            pc = cls(vt, torch.tensor(vn, dtype=torch.float, device=device))
+        else:
+            pc = cls(vt)
+        pc.file_path = file_path
+        return pc
+
+    @classmethod
+    def loadXYZ(cls, file_path: str, device=None) -> "Pointcloud":
+        """Object.py:92-117 (the reference reads into `v_list` but converts an undefined `v`; fixed here)."""
+        path = Path(file_path)
+        assert path.is_file()
+        assert path.suffix in (".xyz", ".clean_xyz")
+        device = device if device is not None else _default_device()
+        pts = np.loadtxt(file_path, dtype=np.float64, usecols=(0, 1, 2)).reshape(-1, 3)
+        pc = cls(torch.tensor(pts, dtype=torch.float, device=device))
+        pc.file_path = file_path
+        return pc

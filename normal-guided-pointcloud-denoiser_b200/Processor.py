@@ -1,0 +1,169 @@
+"""Orchestration with the interface of the reference's Pointcloud/Modules/Processor.py (:24-199).
+`denoise` and `denoiseUntilMinimumError` run on the fused tree-order session of libngpd; the step-by-step
+public operators (Selector / Decompositionor / Denoiser) give the same results and remain available for
+callers that compose their own loops, as the reference notebooks do."""
+from __future__ import annotations
+
+import math
+from typing import Callable
+
+import torch
+
+from . import _lib
+from .Decompositionor import Decompositionor
+from .Denoiser import Denoiser
+from .GraphBuilder import GraphBuilder
+from .Noise import Noise
+from .Object import Pointcloud
+from .Selector import Selector
+from .Utils import TorchUtils
+
+
+class Processor:
+    def __init__(self, pointcloud: Pointcloud):
+        self.pointcloud = pointcloud
+        self.graphBuilder = GraphBuilder(pointcloud)
+        graph = self.graphBuilder.graph
+        self.graph = graph
+        self.selector = Selector(graph)
+        self.noise = Noise(graph)
+        self.denoiser = Denoiser(graph)
+        self.decompositionor = Decompositionor(graph)
+        self._session = None
+
+    # ---- fused path -----------------------------------------------------------------------------------
+    def _get_session(self) -> _lib.Session:
+        if self._session is None:
+            self._session = _lib.Session(self.selector.tree_pos, k_hint=16)
+        return self._session
+
+    def _kind_of(self, func) -> int | None:
+        d = self.denoiser
+        table = {d.flat_step: _lib.STEP_FLAT, d.edge_step: _lib.STEP_EDGE, d.feature_step: _lib.STEP_FEATURE,
+                 d.corner_step: _lib.STEP_CORNER, d.dummy_step: _lib.STEP_NONE}
+        return table.get(func)
+
+    def _mean_edge_length(self, k: int) -> float:
+        s, c = self._get_session().mean_edge_length_parts(k)
+        return float(torch.tensor(s / c, dtype=torch.float32))
+
+    # ---- reference interface ----------------------------------------------------------------------------
+    def getMyFeatureDecomposition(self, N: int = 2 ** 4, angle: float = None):
+        """(:110-117) NVT on the current normals -> eigen-space smoothing -> NVT on the smoothed normals."""
+        angle = angle if angle is not None else math.pi * 5 / 12
+        n = self.graph.n
+        selection = self.selector.getKNNSelection(N)
+        nvt = self.decompositionor.getBetterFilteredNVT(selection, n, angle)
+        filtered_normals = nvt.getVUSmoothedNormals(n)
+        decomposition = self.decompositionor.getBetterFilteredNVT(selection, filtered_normals, angle)
+        return decomposition, filtered_normals
+
+    def denoise(self):
+        """(:119-139) d = 2 * mean 6-NN edge length; two iterations; flat / edge / feature steps with
+        alpha (1, .2, 1); positions are updated in place, graph.n becomes the smoothed normals."""
+        g = self.graph
+        sess = self._get_session()
+        sess.set_state(g.pos, g.n)
+        d = 2.0 * self._mean_edge_length(6)
+        params = _lib.make_params(16, 8, None, 0.3, 3.0, 0.2, (_lib.STEP_FLAT, _lib.STEP_EDGE, _lib.STEP_FEATURE), (1.0, 0.2, 1.0), d)
+        for _ in range(2):
+            sess.step(params)
+        pos, nrm, _ = sess.get_state(False)
+        g.pos.copy_(pos)
+        g.n = nrm
+
+    def denoiseUntilMinimumError(self, gt_pos: torch.Tensor, strategy: dict, k: int = 7, alpha: list = [0.02, 0.02, 0.1],
+                                 d: float = 200, error_funcs: list[Callable] = [TorchUtils.PaperDistance]):
+        """(:141-185) iterate while mean(error_funcs[0](gt, pos)) decreases.  Returns (positions, errors,
+        iteration count) with the reference's bookkeeping: the returned positions are those of the LAST
+        iteration when at least two ran (the reference's previous_pos aliases graph.pos, :174-175), the noisy input
+        otherwise; graph.pos / graph.n are reset to the noisy input on exit.  A class holding exactly one point is
+        updated normally (the reference raises IndexError there, :163)."""
+        g = self.graph
+        noisy_pos, noisy_n = g.pos.clone(), g.n.clone()
+        kinds = [_lib.STEP_NONE] * 3
+        fused = True
+        for key, func in strategy.items():
+            kind = self._kind_of(func)
+            if kind is None or key not in (0, 1, 2):
+                fused = False
+            else:
+                kinds[key] = kind
+        i = 0
+        previous_pos = current_pos = noisy_pos
+        previous_error = [f(gt_pos, g.pos) + 200 for f in error_funcs]
+        current_error = [f(gt_pos, g.pos) for f in error_funcs]
+        if fused:
+            sess = self._get_session()
+            sess.set_state(g.pos, g.n)
+            params = _lib.make_params(16, k, None, 0.3, 3.0, 0.2, kinds, [alpha[q] if q < len(alpha) else 0.0 for q in range(3)], float(d))
+        while current_error[0].mean(dim=0) < previous_error[0].mean(dim=0):
+            if fused:
+                sess.step(params)
+                pos, f_n, _ = sess.get_state(False)
+                g.pos.copy_(pos)
+            else:
+                f_n = self._generic_iteration(strategy, k, alpha, d)
+            error = [f(gt_pos, g.pos) for f in error_funcs]
+            previous_error, current_error = current_error, error
+            previous_pos, current_pos = current_pos, g.pos
+            g.n = f_n
+            i += 1
+        print(f"Stopped cause new error was {current_error[0].mean(dim=0):.2E} compaired to previous error {previous_error[0].mean(dim=0):.2E}")
+        g.pos = noisy_pos
+        g.n = noisy_n
+        return previous_pos, previous_error, i - 1
+
+    def _generic_iteration(self, strategy: dict, k: int, alpha, d):
+        """One iteration through the public operators, for strategies holding callables that are not Denoiser steps."""
+        g = self.graph
+        decomposition, f_n = self.getMyFeatureDecomposition()
+        edge_vectors = decomposition.eigvec[..., 0]
+        classes = decomposition.getClasses()
+        selection = self.selector.getKNNSelection(k)
+        for key, func in strategy.items():
+            indices = (classes == key).nonzero().flatten()
+            if indices.size(0) == 0:
+                continue
+            if func == self.denoiser.edge_step:
+                new_pos = func(selection.filter(indices), f_n, edge_vectors, d, alpha[key])
+            else:
+                new_pos = func(selection.filter(indices), f_n, d, alpha[key])
+            g.pos[indices] = new_pos
+        return f_n
+
+    def denoise_unfused(self):
+        """Processor.denoise written against the public operators, call for call as the reference does it
+        (:119-139); used to cross-check the fused session."""
+        g = self.graph
+        l = TorchUtils.averageEdgeLength(g.pos, self.selector.getKNNSelection(6).getEdgeIndex())
+        d = float(2 * l)
+        alphas = [1, 0.2, 1]
+        for _ in range(2):
+            decomposition, f_n = self.getMyFeatureDecomposition()
+            classes = decomposition.getClasses()
+            selection = self.selector.getKNNSelection(8)
+            for key in range(3):
+                indices = (classes == key).nonzero().flatten()
+                if indices.size(0) == 0:
+                    continue
+                if key == 0:
+                    new_pos = self.denoiser.flat_step(selection.filter(indices), f_n, d, alphas[key])
+                elif key == 1:
+                    new_pos = self.denoiser.edge_step(selection.filter(indices), f_n, decomposition.eigvec[..., 0], d, alphas[key])
+                else:
+                    new_pos = self.denoiser.feature_step(selection.filter(indices), f_n, d, alphas[key])
+                g.pos[indices] = new_pos
+            g.n = f_n
+
+    def preprocessPointcloud(self, k: int = 12, noise_level: float = 0.3):
+        """(:187-199) kNN graph + PCA normals on the clean cloud, Gaussian noise along the normal of
+        sigma = noise_level * mean edge length, then normals of the noisy cloud over the clean cloud's graph,
+        oriented by the spanning tree."""
+        g = self.graph
+        gb = self.graphBuilder
+        g.edge_index = gb.getKNNEdgeIndex(k)
+        gb.setAndFlipNormals(flip=False)
+        l = TorchUtils.averageEdgeLength(g.pos, g.edge_index)
+        self.noise.generateNoise(noise_level, l, keepNormals=False)
+        gb.setAndFlipNormals(flip=True)

@@ -1,0 +1,123 @@
+#include "knn.cuh"
+#include "../../include/ngpd.h"
+
+namespace ngpd {
+
+// out_mode 0: original indices (public ABI), 1: tree positions (fused session)
+template <int K>
+__global__ void __launch_bounds__(128) knn_kernel(GridView g, const float* __restrict__ query, const int32_t* __restrict__ qorder,
+                                                  int64_t m, int k, int skip_self, int32_t* __restrict__ idx_out,
+                                                  float* __restrict__ d2_out) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m) return;
+    int64_t qi = qorder ? (int64_t)qorder[t] : t;
+    double qx = (double)__ldg(query + 3 * qi), qy = (double)__ldg(query + 3 * qi + 1), qz = (double)__ldg(query + 3 * qi + 2);
+    TopK<K> top;
+    top.init();
+    knn_search<K>(top, g, qx, qy, qz, skip_self ? (int)qi : -1);
+    int32_t* row = idx_out + qi * k;
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+        if (a < k) {
+            int j = top.id[a];
+            row[a] = j >= 0 ? __float_as_int(__ldg(&g.pts[j].w)) : g.n;
+            if (d2_out) d2_out[qi * k + a] = j >= 0 ? (float)top.d[a] : INFINITY;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) nn_sqdist_kernel(GridView g, const float* __restrict__ query, const int32_t* __restrict__ qorder,
+                                                        int64_t m, float* __restrict__ d2_out, int32_t* __restrict__ idx_out) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m) return;
+    int64_t qi = qorder ? (int64_t)qorder[t] : t;
+    float fx = __ldg(query + 3 * qi), fy = __ldg(query + 3 * qi + 1), fz = __ldg(query + 3 * qi + 2);
+    TopK<1> top;
+    top.init();
+    knn_search<1>(top, g, (double)fx, (double)fy, (double)fz, -1);
+    int j = top.id[0];
+    float4 p = __ldg(g.pts + (j >= 0 ? j : 0));
+    // fp32 recomputation, as the reference does after its 1-NN lookup (Utils.py:262-263)
+    float dx = p.x - fx, dy = p.y - fy, dz = p.z - fz;
+    if (d2_out) d2_out[qi] = (dx * dx + dy * dy) + dz * dz;
+    if (idx_out) idx_out[qi] = j >= 0 ? __float_as_int(p.w) : g.n;
+}
+
+__global__ void __launch_bounds__(256) order_from_vals_kernel(const uint32_t* __restrict__ vals, int64_t m, int32_t* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) out[i] = (int32_t)vals[i];
+}
+__global__ void __launch_bounds__(256) order_from_pts_kernel(const float4* __restrict__ pts, int64_t m, int32_t* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) out[i] = __float_as_int(pts[i].w);
+}
+
+// visiting order of the queries: tree order when query i is tree point i, otherwise sorted by the
+// queries' own cell keys; nullptr (identity) for small or already coherent batches
+static int make_query_order(const ngpd_grid* G, const float* query, int64_t m, int flags, cudaStream_t stream, int32_t** order) {
+    *order = nullptr;
+    if ((flags & NGPD_KNN_COHERENT) || m < 2048) return 0;
+    NGPD_CUDA_OK(cudaMallocAsync(order, m * sizeof(int32_t), stream));
+    if ((flags & NGPD_KNN_QUERY_IS_TREE) && m == G->n) {
+        order_from_pts_kernel<<<(unsigned)cdiv(m, 256), 256, 0, stream>>>(G->pts, m, *order);
+        NGPD_CUDA_OK(cudaGetLastError());
+        return 0;
+    }
+    uint64_t *keys = nullptr, *keys2 = nullptr;
+    uint32_t *vals = nullptr, *vals2 = nullptr;
+    NGPD_CUDA_OK(cudaMallocAsync(&keys, m * 8, stream)); NGPD_CUDA_OK(cudaMallocAsync(&keys2, m * 8, stream));
+    NGPD_CUDA_OK(cudaMallocAsync(&vals, m * 4, stream)); NGPD_CUDA_OK(cudaMallocAsync(&vals2, m * 4, stream));
+    int rc = point_keys(G->v, query, m, keys, vals, stream);
+    if (rc) return rc;
+    bool in_tmp = false;
+    rc = radix_sort_pairs(keys, vals, keys2, vals2, m, key_bits(G->v), stream, &in_tmp);
+    if (rc) return rc;
+    order_from_vals_kernel<<<(unsigned)cdiv(m, 256), 256, 0, stream>>>(in_tmp ? vals2 : vals, m, *order);
+    NGPD_CUDA_OK(cudaGetLastError());
+    cudaFreeAsync(keys, stream); cudaFreeAsync(keys2, stream); cudaFreeAsync(vals, stream); cudaFreeAsync(vals2, stream);
+    return 0;
+}
+
+template <int K>
+static void launch_knn(const ngpd_grid* G, const float* query, const int32_t* order, int64_t m, int k, int skip, int32_t* idx, float* d2, cudaStream_t s) {
+    knn_kernel<K><<<(unsigned)cdiv(m, 128), 128, 0, s>>>(G->v, query, order, m, k, skip, idx, d2);
+}
+
+}  // namespace ngpd
+
+using namespace ngpd;
+
+extern "C" __attribute__((visibility("default"))) int ngpd_knn(const ngpd_grid_t* G, const float* query, int64_t m, int k, int flags,
+                        int32_t* idx_out, float* d2_out, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    NGPD_REQUIRE(G && query && idx_out, "ngpd_knn: NULL argument");
+    NGPD_REQUIRE(k >= 1 && k <= 64, "ngpd_knn: k must be in [1, 64]");
+    if (m <= 0) return 0;
+    int32_t* order = nullptr;
+    int rc = make_query_order(G, query, m, flags, stream, &order);
+    if (rc) return rc;
+    int skip = (flags & NGPD_KNN_SKIP_SELF) ? 1 : 0;
+    if (k <= 1) launch_knn<1>(G, query, order, m, k, skip, idx_out, d2_out, stream);
+    else if (k <= 4) launch_knn<4>(G, query, order, m, k, skip, idx_out, d2_out, stream);
+    else if (k <= 8) launch_knn<8>(G, query, order, m, k, skip, idx_out, d2_out, stream);
+    else if (k <= 16) launch_knn<16>(G, query, order, m, k, skip, idx_out, d2_out, stream);
+    else if (k <= 32) launch_knn<32>(G, query, order, m, k, skip, idx_out, d2_out, stream);
+    else launch_knn<64>(G, query, order, m, k, skip, idx_out, d2_out, stream);
+    NGPD_CUDA_OK(cudaGetLastError());
+    if (order) NGPD_CUDA_OK(cudaFreeAsync(order, stream));
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int ngpd_nn_sqdist(const ngpd_grid_t* G, const float* query, int64_t m, int flags,
+                              float* d2_out, int32_t* idx_out, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    NGPD_REQUIRE(G && query, "ngpd_nn_sqdist: NULL argument");
+    if (m <= 0) return 0;
+    int32_t* order = nullptr;
+    int rc = make_query_order(G, query, m, flags, stream, &order);
+    if (rc) return rc;
+    nn_sqdist_kernel<<<(unsigned)cdiv(m, 128), 128, 0, stream>>>(G->v, query, order, m, d2_out, idx_out);
+    NGPD_CUDA_OK(cudaGetLastError());
+    if (order) NGPD_CUDA_OK(cudaFreeAsync(order, stream));
+    return 0;
+}

@@ -1,0 +1,455 @@
+// Fused denoising session: the body of Processor.denoise / denoiseUntilMinimumError
+// (Processor.py:124-139, 158-176) on device-resident state kept in TREE (Morton) order as float4 arrays,
+// so that a point's neighbours are close in memory and every gather is one 16-byte load that hits L1/L2.
+//   step = knn(k_f) -> [NVT -> eigh -> smooth] -> [NVT -> eigh -> label, edge vector]
+//          -> per class in order 0,1,2: (flat only: cloud-wide centre/delta) -> update into the ping-pong buffer
+// Semantics kept from the reference: the index is frozen on the construction-time positions while queries
+// are the current positions; the k_u-neighbourhood is the prefix of the k_f one; classes are updated
+// one after the other, each from a snapshot that already contains the earlier classes' moves.
+// `owned` (optional) marks the rows this rank computes; the remaining rows are halo copies of points owned by
+// another GPU, refreshed between phases by ngpd_session_{export,import}_rows.
+#include <vector>
+#include "knn.cuh"
+#include "point_math.cuh"
+#include "../../include/ngpd.h"
+
+struct ngpd_session {
+    ngpd_grid* grid = nullptr;
+    int64_t n = 0;
+    float4* pos[2] = {nullptr, nullptr};
+    int cur = 0;
+    float4* nrm = nullptr;    // current normals
+    float4* fn = nullptr;     // smoothed normals of this step
+    float4* edge = nullptr;   // crease direction (eigenvector of the smallest stage-2 eigenvalue)
+    uint8_t* label = nullptr;
+    uint8_t* owned = nullptr; // nullable
+    int32_t* idx = nullptr;
+    int idx_k = 0;
+    double* acc = nullptr;    // 4 doubles
+    float* cd = nullptr;      // centre xyz, delta
+    int launches = 0;
+};
+
+namespace ngpd {
+
+template <int K>
+__global__ void __launch_bounds__(128) session_knn_kernel(GridView g, const float4* __restrict__ pos, const uint8_t* __restrict__ owned,
+                                                          int64_t n, int k, int32_t* __restrict__ idx) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    if (owned && !owned[s]) return;
+    float4 q = __ldg(pos + s);
+    TopK<K> top;
+    top.init();
+    knn_search<K>(top, g, (double)q.x, (double)q.y, (double)q.z, -1);
+    int32_t* row = idx + s * k;
+#pragma unroll
+    for (int a = 0; a < K; ++a)
+        if (a < k) row[a] = top.id[a] >= 0 ? top.id[a] : (int32_t)s;   // fewer than k tree points: pad with self
+}
+
+// stage 1: filtered NVT on the current normals, smoothed normal out
+__global__ void __launch_bounds__(128) session_nvt_smooth_kernel(Quad4 pos, Quad4 nrm, const uint8_t* __restrict__ owned,
+                                                                 const int32_t* __restrict__ idx, int64_t n, int k, float x_thresh,
+                                                                 float tau, float damp, float4* __restrict__ fn) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    if (owned && !owned[s]) return;
+    NvtResult o;
+    nvt_point(pos, nrm, s, idx + s * k, k, x_thresh, o, nullptr);
+    V3 f = smooth_normal(o.w, o.V, nrm(s), tau, damp);
+    fn[s] = make_float4(f.x, f.y, f.z, 0.0f);
+}
+
+// stage 2: filtered NVT on the smoothed normals, label + crease direction out
+__global__ void __launch_bounds__(128) session_nvt_classify_kernel(Quad4 pos, Quad4 fn, const uint8_t* __restrict__ owned,
+                                                                   const int32_t* __restrict__ idx, int64_t n, int k, float x_thresh,
+                                                                   float scale, uint8_t* __restrict__ label, float4* __restrict__ edge) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    if (owned && !owned[s]) return;
+    NvtResult o;
+    nvt_point(pos, fn, s, idx + s * k, k, x_thresh, o, nullptr);
+    label[s] = (uint8_t)classify(o.w, scale);
+    edge[s] = make_float4(o.V[0], o.V[3], o.V[6], 0.0f);
+}
+
+// flat_step scalars over the neighbour multiset of one class (Denoiser.py:106-107)
+__global__ void __launch_bounds__(256) session_class_sum_kernel(Quad4 pos, const uint8_t* __restrict__ owned, const uint8_t* __restrict__ label,
+                                                                int key, const int32_t* __restrict__ idx, int64_t n, int k, int ku,
+                                                                double* __restrict__ acc) {
+    double sx = 0, sy = 0, sz = 0, cnt = 0;
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += (int64_t)gridDim.x * blockDim.x) {
+        if ((owned && !owned[s]) || label[s] != key) continue;
+        const int32_t* row = idx + s * k;
+        for (int a = 0; a < ku; ++a) { V3 p = pos((int64_t)row[a]); sx += p.x; sy += p.y; sz += p.z; }
+        cnt += ku;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sx += __shfl_xor_sync(0xffffffffu, sx, o); sy += __shfl_xor_sync(0xffffffffu, sy, o);
+        sz += __shfl_xor_sync(0xffffffffu, sz, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if ((threadIdx.x & 31) == 0 && cnt > 0) { atomicAdd(acc, sx); atomicAdd(acc + 1, sy); atomicAdd(acc + 2, sz); atomicAdd(acc + 3, cnt); }
+}
+__global__ void session_center_kernel(const double* __restrict__ acc, float* __restrict__ cd) {
+    double c = acc[3] > 0 ? acc[3] : 1.0;
+    cd[0] = (float)(acc[0] / c); cd[1] = (float)(acc[1] / c); cd[2] = (float)(acc[2] / c); cd[3] = 0.0f;
+}
+__global__ void __launch_bounds__(256) session_class_max_kernel(Quad4 pos, const uint8_t* __restrict__ owned, const uint8_t* __restrict__ label,
+                                                                int key, const int32_t* __restrict__ idx, int64_t n, int k, int ku,
+                                                                float* __restrict__ cd) {
+    V3 c = v3(cd[0], cd[1], cd[2]);
+    float mx = 0.0f;
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += (int64_t)gridDim.x * blockDim.x) {
+        if ((owned && !owned[s]) || label[s] != key) continue;
+        const int32_t* row = idx + s * k;
+        for (int a = 0; a < ku; ++a) mx = fmaxf(mx, norm3_fma(pos((int64_t)row[a]) - c));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) atomicMax((int*)(cd + 3), __float_as_int(mx));
+}
+
+// one class: members move, everybody else is copied through to the other buffer (snapshot semantics)
+__global__ void __launch_bounds__(128) session_update_kernel(int kind, int key, Quad4 pos, Quad4 fn, const float4* __restrict__ edge,
+                                                             const uint8_t* __restrict__ label, const uint8_t* __restrict__ owned,
+                                                             const int32_t* __restrict__ idx, int64_t n, int k, int ku, float alpha, float dmax,
+                                                             const float* __restrict__ cd, float4* __restrict__ out) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    V3 p = pos(s);
+    if (label[s] == key && (!owned || owned[s])) {
+        const int32_t* row = idx + s * k;
+        if (kind == NGPD_STEP_FLAT) p = flat_point(pos, fn, s, row, ku, cd[3], alpha, dmax);
+        else if (kind == NGPD_STEP_EDGE) { float4 e = __ldg(edge + s); p = edge_point(pos, fn, v3(e.x, e.y, e.z), s, row, ku, alpha, dmax); }
+        else if (kind == NGPD_STEP_FEATURE) p = feature_point(pos, fn, s, row, ku, alpha, dmax);
+        else if (kind == NGPD_STEP_CORNER) p = corner_point(pos, fn, s, row, ku, alpha, dmax);
+    }
+    out[s] = make_float4(p.x, p.y, p.z, 0.0f);
+}
+
+__global__ void __launch_bounds__(256) session_scatter_in_kernel(const float4* __restrict__ tree_pts, const float* __restrict__ pos,
+                                                                 const float* __restrict__ nrm, int64_t n, float4* __restrict__ pos4,
+                                                                 float4* __restrict__ nrm4) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    int64_t o = (int64_t)__float_as_int(__ldg(&tree_pts[s].w));
+    if (pos) pos4[s] = make_float4(__ldg(pos + 3 * o), __ldg(pos + 3 * o + 1), __ldg(pos + 3 * o + 2), 0.0f);
+    if (nrm) nrm4[s] = make_float4(__ldg(nrm + 3 * o), __ldg(nrm + 3 * o + 1), __ldg(nrm + 3 * o + 2), 0.0f);
+}
+__global__ void __launch_bounds__(256) session_scatter_out_kernel(const float4* __restrict__ tree_pts, const float4* __restrict__ pos4,
+                                                                  const float4* __restrict__ nrm4, const uint8_t* __restrict__ label, int64_t n,
+                                                                  float* __restrict__ pos, float* __restrict__ nrm, uint8_t* __restrict__ lab) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    int64_t o = (int64_t)__float_as_int(__ldg(&tree_pts[s].w));
+    if (pos) { float4 p = pos4[s]; pos[3 * o] = p.x; pos[3 * o + 1] = p.y; pos[3 * o + 2] = p.z; }
+    if (nrm) { float4 p = nrm4[s]; nrm[3 * o] = p.x; nrm[3 * o + 1] = p.y; nrm[3 * o + 2] = p.z; }
+    if (lab) lab[o] = label[s];
+}
+
+__global__ void __launch_bounds__(256) session_edge_len_kernel(Quad4 pos, const uint8_t* __restrict__ owned, const int32_t* __restrict__ idx,
+                                                               int64_t n, int k, double* __restrict__ out2) {
+    double sum = 0, cnt = 0;
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += (int64_t)gridDim.x * blockDim.x) {
+        if (owned && !owned[s]) continue;
+        V3 c = pos(s);
+        for (int a = 0; a < k; ++a) sum += (double)norm3_fma(pos((int64_t)idx[s * k + a]) - c);
+        cnt += k;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
+    if ((threadIdx.x & 31) == 0 && cnt > 0) { atomicAdd(out2, sum); atomicAdd(out2 + 1, cnt); }
+}
+
+// halo traffic: rows listed by tree position
+__global__ void __launch_bounds__(256) session_export_kernel(const float4* __restrict__ src, const int32_t* __restrict__ rows, int64_t m,
+                                                             float4* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) out[i] = src[rows[i]];
+}
+__global__ void __launch_bounds__(256) session_import_kernel(float4* __restrict__ dst, const int32_t* __restrict__ rows, int64_t m,
+                                                             const float4* __restrict__ in) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) dst[rows[i]] = in[i];
+}
+
+static inline unsigned strided(int64_t n, int threads) {
+    int64_t b = cdiv(n, threads), cap = (int64_t)num_sms() * 8;
+    return (unsigned)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+static int ensure_idx(ngpd_session* S, int k) {
+    if (S->idx && S->idx_k >= k) return 0;
+    if (S->idx) cudaFree(S->idx);
+    S->idx = nullptr;
+    NGPD_CUDA_OK(cudaMalloc(&S->idx, (size_t)S->n * k * sizeof(int32_t)));
+    S->idx_k = k;
+    return 0;
+}
+
+static int run_knn(ngpd_session* S, int k, int32_t* idx, cudaStream_t st) {
+    unsigned b = (unsigned)cdiv(S->n, 128);
+    const GridView& g = S->grid->v;
+    const float4* p = S->pos[S->cur];
+    if (k <= 4) session_knn_kernel<4><<<b, 128, 0, st>>>(g, p, S->owned, S->n, k, idx);
+    else if (k <= 8) session_knn_kernel<8><<<b, 128, 0, st>>>(g, p, S->owned, S->n, k, idx);
+    else if (k <= 16) session_knn_kernel<16><<<b, 128, 0, st>>>(g, p, S->owned, S->n, k, idx);
+    else if (k <= 32) session_knn_kernel<32><<<b, 128, 0, st>>>(g, p, S->owned, S->n, k, idx);
+    else session_knn_kernel<64><<<b, 128, 0, st>>>(g, p, S->owned, S->n, k, idx);
+    NGPD_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace ngpd
+
+using namespace ngpd;
+
+extern "C" __attribute__((visibility("default"))) int ngpd_session_destroy(ngpd_session_t* S) {
+    if (!S) return 0;
+    if (S->grid) ngpd_grid_destroy(S->grid);
+    void* bufs[] = {S->pos[0], S->pos[1], S->nrm, S->fn, S->edge, S->label, S->owned, S->idx, S->acc, S->cd};
+    for (void* b : bufs) if (b) cudaFree(b);
+    delete S;
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int ngpd_session_create(const float* tree_pos, int64_t n, int k_hint, void* stream_, ngpd_session_t** out) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    NGPD_REQUIRE(out, "ngpd_session_create: out is NULL");
+    *out = nullptr;
+    ngpd_grid* G = nullptr;
+    int rc = ngpd_grid_create(tree_pos, n, 0.0f, k_hint, stream_, &G);
+    if (rc) return rc;
+    ngpd_session* S = new ngpd_session();
+    S->grid = G; S->n = n;
+    size_t b4 = (size_t)n * sizeof(float4);
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = cudaMalloc(&S->pos[0], b4);
+    if (e == cudaSuccess) e = cudaMalloc(&S->pos[1], b4);
+    if (e == cudaSuccess) e = cudaMalloc(&S->nrm, b4);
+    if (e == cudaSuccess) e = cudaMalloc(&S->fn, b4);
+    if (e == cudaSuccess) e = cudaMalloc(&S->edge, b4);
+    if (e == cudaSuccess) e = cudaMalloc(&S->label, (size_t)n);
+    if (e == cudaSuccess) e = cudaMalloc(&S->acc, 4 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&S->cd, 4 * sizeof(float));
+    if (e != cudaSuccess) { set_error("ngpd_session_create: %s", cudaGetErrorString(e)); ngpd_session_destroy(S); return -2; }
+    NGPD_CUDA_OK(cudaMemsetAsync(S->label, 0, (size_t)n, st));
+    NGPD_CUDA_OK(cudaMemsetAsync(S->nrm, 0, b4, st));
+    // current positions start as the tree positions
+    session_scatter_in_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(G->pts, tree_pos, nullptr, n, S->pos[0], nullptr);
+    NGPD_CUDA_OK(cudaGetLastError());
+    *out = S;
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int ngpd_session_set_state(ngpd_session_t* S, const float* pos, const float* nrm, void* stream_) {
+    NGPD_REQUIRE(S, "ngpd_session_set_state: NULL session");
+    session_scatter_in_kernel<<<(unsigned)cdiv(S->n, 256), 256, 0, (cudaStream_t)stream_>>>(S->grid->pts, pos, nrm, S->n, S->pos[S->cur], S->nrm);
+    NGPD_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int ngpd_session_get_state(ngpd_session_t* S, float* pos_out, float* nrm_out, uint8_t* labels_out, void* stream_) {
+    NGPD_REQUIRE(S, "ngpd_session_get_state: NULL session");
+    session_scatter_out_kernel<<<(unsigned)cdiv(S->n, 256), 256, 0, (cudaStream_t)stream_>>>(S->grid->pts, S->pos[S->cur], S->nrm, S->label, S->n,
+                                                                                             pos_out, nrm_out, labels_out);
+    NGPD_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int ngpd_session_set_owned(ngpd_session_t* S, const uint8_t* owned_tree_order, void* stream_) {
+    NGPD_REQUIRE(S, "ngpd_session_set_owned: NULL session");
+    if (!owned_tree_order) { if (S->owned) cudaFree(S->owned); S->owned = nullptr; return 0; }
+    if (!S->owned) NGPD_CUDA_OK(cudaMalloc(&S->owned, (size_t)S->n));
+    NGPD_CUDA_OK(cudaMemcpyAsync(S->owned, owned_tree_order, (size_t)S->n, cudaMemcpyDeviceToDevice, (cudaStream_t)stream_));
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int ngpd_session_order(const ngpd_session_t* S, int32_t* perm_out, void* stream_) {
+    NGPD_REQUIRE(S, "ngpd_session_order: NULL session");
+    return ngpd_grid_order(S->grid, perm_out, stream_);
+}
+
+extern "C" __attribute__((visibility("default"))) int ngpd_session_launch_count(const ngpd_session_t* S) { return S ? S->launches : 0; }
+
+// ---- phases (exposed one by one so that a multi-GPU driver can exchange halos in between) -----------
+extern "C" __attribute__((visibility("default"))) int ngpd_session_phase_features(ngpd_session_t* S, const ngpd_step_params_t* p, int part, void* stream_) {
+    // part 0: knn + NVT + smoothing (writes fn);  part 1: NVT on fn + labels + crease direction
+    cudaStream_t st = (cudaStream_t)stream_;
+    NGPD_REQUIRE(S && p, "ngpd_session_phase_features: NULL argument");
+    const int kf = p->k_feature;
+    NGPD_REQUIRE(kf >= 1 && kf <= 64 && p->k_update >= 1 && p->k_update <= kf, "ngpd_session: need 1 <= k_update <= k_feature <= 64");
+    unsigned b = (unsigned)cdiv(S->n, 128);
+    Quad4 pos{S->pos[S->cur]};
+    if (part == 0) {
+        int rc = ensure_idx(S, kf);
+        if (rc) return rc;
+        S->idx_k = kf;
+        rc = run_knn(S, kf, S->idx, st);
+        if (rc) return rc;
+        session_nvt_smooth_kernel<<<b, 128, 0, st>>>(pos, Quad4{S->nrm}, S->owned, S->idx, S->n, kf, p->x_thresh, p->tau, p->damp, S->fn);
+        S->launches += 2;
+    } else {
+        session_nvt_classify_kernel<<<b, 128, 0, st>>>(pos, Quad4{S->fn}, S->owned, S->idx, S->n, kf, p->x_thresh, p->scale, S->label, S->edge);
+        S->launches += 1;
+    }
+    NGPD_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// flat-step scalars of class `key`: part 0 accumulates {sum xyz, count} into acc (4 doubles, device), part 1
+// turns acc into the centre and accumulates the max distance.  Between the parts a multi-GPU driver all-reduces
+// acc (sum) and afterwards cd[3] (max).
+extern "C" __attribute__((visibility("default"))) int ngpd_session_phase_flat_scalars(ngpd_session_t* S, const ngpd_step_params_t* p, int key, int part, void* stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    NGPD_REQUIRE(S && p, "ngpd_session_phase_flat_scalars: NULL argument");
+    Quad4 pos{S->pos[S->cur]};
+    if (part == 0) {
+        NGPD_CUDA_OK(cudaMemsetAsync(S->acc, 0, 4 * sizeof(double), st));
+        session_class_sum_kernel<<<strided(S->n, 256), 256, 0, st>>>(pos, S->owned, S->label, key, S->idx, S->n, S->idx_k, p->k_update, S->acc);
+        S->launches += 1;
+    } else {
+        session_center_kernel<<<1, 1, 0, st>>>(S->acc, S->cd);
+        session_class_max_kernel<<<strided(S->n, 256), 256, 0, st>>>(pos, S->owned, S->label, key, S->idx, S->n, S->idx_k, p->k_update, S->cd);
+        S->launches += 2;
+    }
+    NGPD_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int ngpd_session_phase_update(ngpd_session_t* S, const ngpd_step_params_t* p, int key, void* stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    NGPD_REQUIRE(S && p && key >= 0 && key < 3, "ngpd_session_phase_update: bad argument");
+    int kind = p->strategy[key];
+    if (kind < 0) return 0;
+    session_update_kernel<<<(unsigned)cdiv(S->n, 128), 128, 0, st>>>(kind, key, Quad4{S->pos[S->cur]}, Quad4{S->fn}, S->edge, S->label, S->owned,
+                                                                     S->idx, S->n, S->idx_k, p->k_update, p->alpha[key], p->dmax, S->cd,
+                                                                     S->pos[S->cur ^ 1]);
+    NGPD_CUDA_OK(cudaGetLastError());
+    S->cur ^= 1;
+    S->launches += 1;
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int ngpd_session_phase_commit_normals(ngpd_session_t* S) {
+    NGPD_REQUIRE(S, "ngpd_session_phase_commit_normals: NULL session");
+    float4* t = S->nrm; S->nrm = S->fn; S->fn = t;   // graph.n = f_n  (Processor.py:139)
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int ngpd_session_step(ngpd_session_t* S, const ngpd_step_params_t* p, void* stream_) {
+    NGPD_REQUIRE(S && p, "ngpd_session_step: NULL argument");
+    S->launches = 0;
+    int rc;
+    if ((rc = ngpd_session_phase_features(S, p, 0, stream_))) return rc;
+    if ((rc = ngpd_session_phase_features(S, p, 1, stream_))) return rc;
+    for (int key = 0; key < 3; ++key) {
+        if (p->strategy[key] < 0) continue;
+        if (p->strategy[key] == NGPD_STEP_FLAT) {
+            if ((rc = ngpd_session_phase_flat_scalars(S, p, key, 0, stream_))) return rc;
+            if ((rc = ngpd_session_phase_flat_scalars(S, p, key, 1, stream_))) return rc;
+        }
+        if ((rc = ngpd_session_phase_update(S, p, key, stream_))) return rc;
+    }
+    return ngpd_session_phase_commit_normals(S);
+}
+
+extern "C" __attribute__((visibility("default"))) int ngpd_session_mean_edge_length(ngpd_session_t* S, int k, double* out_host, void* stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    NGPD_REQUIRE(S && out_host && k >= 1 && k <= 64, "ngpd_session_mean_edge_length: bad argument");
+    int32_t* idx = nullptr;
+    double* acc = nullptr;
+    NGPD_CUDA_OK(cudaMallocAsync(&idx, (size_t)S->n * k * sizeof(int32_t), st));
+    NGPD_CUDA_OK(cudaMallocAsync(&acc, 2 * sizeof(double), st));
+    NGPD_CUDA_OK(cudaMemsetAsync(acc, 0, 2 * sizeof(double), st));
+    int rc = run_knn(S, k, idx, st);
+    if (rc) return rc;
+    session_edge_len_kernel<<<strided(S->n, 256), 256, 0, st>>>(Quad4{S->pos[S->cur]}, S->owned, idx, S->n, k, acc);
+    double h[2];
+    NGPD_CUDA_OK(cudaMemcpyAsync(h, acc, sizeof(h), cudaMemcpyDeviceToHost, st));
+    NGPD_CUDA_OK(cudaStreamSynchronize(st));
+    NGPD_CUDA_OK(cudaFreeAsync(idx, st));
+    NGPD_CUDA_OK(cudaFreeAsync(acc, st));
+    out_host[0] = h[0]; out_host[1] = h[1];   // {sum of edge lengths, edge count}: callers divide (and all-reduce first on multi-GPU)
+    return 0;
+}
+
+// raw device views for a multi-GPU driver and for tests: which = 0 pos, 1 nrm, 2 fn, 3 acc (double*), 4 cd (float*), 5 label, 6 idx
+extern "C" __attribute__((visibility("default"))) void* ngpd_session_buffer(ngpd_session_t* S, int which) {
+    if (!S) return nullptr;
+    switch (which) {
+        case 0: return S->pos[S->cur];
+        case 1: return S->nrm;
+        case 2: return S->fn;
+        case 3: return S->acc;
+        case 4: return S->cd;
+        case 5: return S->label;
+        case 6: return S->idx;
+        default: return nullptr;
+    }
+}
+
+extern "C" __attribute__((visibility("default"))) int ngpd_session_export_rows(ngpd_session_t* S, int which, const int32_t* rows, int64_t m, float* out4, void* stream_) {
+    NGPD_REQUIRE(S && (which >= 0 && which <= 2), "ngpd_session_export_rows: bad argument");
+    if (m <= 0) return 0;
+    const float4* src = which == 0 ? S->pos[S->cur] : (which == 1 ? S->nrm : S->fn);
+    session_export_kernel<<<(unsigned)cdiv(m, 256), 256, 0, (cudaStream_t)stream_>>>(src, rows, m, (float4*)out4);
+    NGPD_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+extern "C" __attribute__((visibility("default"))) int ngpd_session_import_rows(ngpd_session_t* S, int which, const int32_t* rows, int64_t m, const float* in4, void* stream_) {
+    NGPD_REQUIRE(S && (which >= 0 && which <= 2), "ngpd_session_import_rows: bad argument");
+    if (m <= 0) return 0;
+    float4* dst = which == 0 ? S->pos[S->cur] : (which == 1 ? S->nrm : S->fn);
+    session_import_kernel<<<(unsigned)cdiv(m, 256), 256, 0, (cudaStream_t)stream_>>>(dst, rows, m, (const float4*)in4);
+    NGPD_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// End-to-end convenience with HOST buffers (the e2e measurement path): H2D of this step's positions and normals,
+// one or more iterations, D2H of positions, normals and labels.  Synchronous.
+extern "C" __attribute__((visibility("default"))) int ngpd_session_run_host(ngpd_session_t* S, const ngpd_step_params_t* p, int iterations, const float* pos_host,
+                                     const float* nrm_host, float* pos_out_host, float* nrm_out_host, uint8_t* labels_out_host,
+                                     void* stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    NGPD_REQUIRE(S && p && pos_host && nrm_host, "ngpd_session_run_host: NULL argument");
+    size_t b3 = (size_t)S->n * 3 * sizeof(float);
+    float *dpos = nullptr, *dnrm = nullptr;
+    uint8_t* dlab = nullptr;
+    NGPD_CUDA_OK(cudaMallocAsync(&dpos, b3, st));
+    NGPD_CUDA_OK(cudaMallocAsync(&dnrm, b3, st));
+    NGPD_CUDA_OK(cudaMallocAsync(&dlab, (size_t)S->n, st));
+    NGPD_CUDA_OK(cudaMemcpyAsync(dpos, pos_host, b3, cudaMemcpyHostToDevice, st));
+    NGPD_CUDA_OK(cudaMemcpyAsync(dnrm, nrm_host, b3, cudaMemcpyHostToDevice, st));
+    int rc = ngpd_session_set_state(S, dpos, dnrm, stream_);
+    for (int i = 0; i < iterations && !rc; ++i) rc = ngpd_session_step(S, p, stream_);
+    if (!rc) rc = ngpd_session_get_state(S, dpos, dnrm, dlab, stream_);
+    if (rc) return rc;
+    if (pos_out_host) NGPD_CUDA_OK(cudaMemcpyAsync(pos_out_host, dpos, b3, cudaMemcpyDeviceToHost, st));
+    if (nrm_out_host) NGPD_CUDA_OK(cudaMemcpyAsync(nrm_out_host, dnrm, b3, cudaMemcpyDeviceToHost, st));
+    if (labels_out_host) NGPD_CUDA_OK(cudaMemcpyAsync(labels_out_host, dlab, (size_t)S->n, cudaMemcpyDeviceToHost, st));
+    NGPD_CUDA_OK(cudaFreeAsync(dpos, st));
+    NGPD_CUDA_OK(cudaFreeAsync(dnrm, st));
+    NGPD_CUDA_OK(cudaFreeAsync(dlab, st));
+    NGPD_CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int ngpd_denoise_host(const float* tree_pos_host, const float* pos_host, const float* nrm_host, int64_t n,
+                                 const ngpd_step_params_t* p, int iterations, float* pos_out_host, float* nrm_out_host,
+                                 uint8_t* labels_out_host) {
+    NGPD_REQUIRE(tree_pos_host && pos_host && nrm_host && p && n > 0, "ngpd_denoise_host: bad argument");
+    float* dtree = nullptr;
+    size_t b3 = (size_t)n * 3 * sizeof(float);
+    NGPD_CUDA_OK(cudaMalloc(&dtree, b3));
+    NGPD_CUDA_OK(cudaMemcpy(dtree, tree_pos_host, b3, cudaMemcpyHostToDevice));
+    ngpd_session_t* S = nullptr;
+    int rc = ngpd_session_create(dtree, n, p->k_feature, nullptr, &S);
+    cudaFree(dtree);
+    if (rc) return rc;
+    rc = ngpd_session_run_host(S, p, iterations, pos_host, nrm_host, pos_out_host, nrm_out_host, labels_out_host, nullptr);
+    ngpd_session_destroy(S);
+    return rc;
+}

@@ -1,0 +1,39 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def fandisk():
+    import numpy as np
+    return dict(np.load(os.path.join(GOLDEN, "fandisk_denoise.npz")))
+
+
+@pytest.fixture(scope="session")
+def until_min():
+    import numpy as np
+    return dict(np.load(os.path.join(GOLDEN, "until_min.npz")))
+
+
+@pytest.fixture(scope="session")
+def cube():
+    import numpy as np
+    return dict(np.load(os.path.join(GOLDEN, "cube386_labels.npz")))
+
+
+def angle_between(a, b):
+    """fp64 atan2(|a x b|, a.b): fp32 acos has a ~5e-4 rad floor near 0."""
+    import numpy as np
+    a = a.astype(np.float64); b = b.astype(np.float64)
+    return np.arctan2(np.linalg.norm(np.cross(a, b), axis=1), (a * b).sum(1))

@@ -1,0 +1,76 @@
+// TEST-ONLY: compiles the product's per-point math headers (csrc/point_math.cuh, csrc/eig3.cuh) for the host so
+// that the arithmetic can be checked against the golden vectors on a machine without a GPU.  Nothing in the
+// product package loads this library; the CUDA kernels include the very same headers.
+#include <cstdint>
+#include <cmath>
+using std::signbit;
+using std::isfinite;
+#include "../../normal-guided-pointcloud-denoiser_b200/csrc/point_math.cuh"
+
+using namespace ngpd;
+
+struct HostPacked3 {
+    const float* p;
+    V3 operator()(int64_t i) const { return v3(p[3 * i], p[3 * i + 1], p[3 * i + 2]); }
+};
+
+extern "C" {
+
+void hm_eigh3(const float* T, int64_t m, float* w, float* V) {
+    for (int64_t r = 0; r < m; ++r) {
+        const float* a = T + 9 * r;
+        eigh3_lapack(a[0], a[3], a[6], a[4], a[7], a[8], w + 3 * r, V + 9 * r);
+    }
+}
+
+void hm_nvt(const float* pos, const float* nrm, const int32_t* idx, const int32_t* rows, int64_t m, int k, float x_thresh,
+            float* w, float* V, float* T, int32_t* sumw) {
+    HostPacked3 P{pos}, N{nrm};
+    for (int64_t r = 0; r < m; ++r) {
+        NvtResult o;
+        float t6[6];
+        nvt_point(P, N, rows ? (int64_t)rows[r] : r, idx + r * k, k, x_thresh, o, t6);
+        for (int c = 0; c < 3; ++c) w[3 * r + c] = o.w[c];
+        for (int c = 0; c < 9; ++c) V[9 * r + c] = o.V[c];
+        float* t = T + 9 * r;
+        t[0] = t6[0]; t[1] = t6[1]; t[2] = t6[2]; t[3] = t6[1]; t[4] = t6[3]; t[5] = t6[4]; t[6] = t6[2]; t[7] = t6[4]; t[8] = t6[5];
+        sumw[r] = o.sumw;
+    }
+}
+
+void hm_smooth(const float* w, const float* V, const float* nrm, int64_t m, float tau, float damp, float* out) {
+    HostPacked3 N{nrm};
+    for (int64_t r = 0; r < m; ++r) {
+        V3 f = smooth_normal(w + 3 * r, V + 9 * r, N(r), tau, damp);
+        out[3 * r] = f.x; out[3 * r + 1] = f.y; out[3 * r + 2] = f.z;
+    }
+}
+
+void hm_classify(const float* w, int64_t m, float scale, uint8_t* lab) {
+    for (int64_t r = 0; r < m; ++r) lab[r] = (uint8_t)classify(w + 3 * r, scale);
+}
+
+void hm_pca(const float* pos, const int32_t* idx, int64_t m, int k, float* normals) {
+    HostPacked3 P{pos};
+    for (int64_t r = 0; r < m; ++r) {
+        float w[3], V[9];
+        pca_point(P, idx + r * k, k, w, V);
+        normals[3 * r] = V[0]; normals[3 * r + 1] = V[3]; normals[3 * r + 2] = V[6];
+    }
+}
+
+void hm_update(int kind, const float* pos, const float* nrm, const float* edge, const int32_t* idx, const int32_t* rows, int64_t m, int k,
+               float alpha, float dmax, float delta, float* out) {
+    HostPacked3 P{pos}, N{nrm}, E{edge};
+    for (int64_t r = 0; r < m; ++r) {
+        int64_t c = rows ? (int64_t)rows[r] : r;
+        V3 p;
+        if (kind == 0) p = flat_point(P, N, c, idx + r * k, k, delta, alpha, dmax);
+        else if (kind == 1) p = edge_point(P, N, E(c), c, idx + r * k, k, alpha, dmax);
+        else if (kind == 2) p = feature_point(P, N, c, idx + r * k, k, alpha, dmax);
+        else p = corner_point(P, N, c, idx + r * k, k, alpha, dmax);
+        out[3 * r] = p.x; out[3 * r + 1] = p.y; out[3 * r + 2] = p.z;
+    }
+}
+
+}  // extern "C"
