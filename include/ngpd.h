@@ -130,6 +130,11 @@ int ngpd_session_step(ngpd_session_t* s, const ngpd_step_params_t* p, void* stre
 /* k-NN edge lengths of the current positions incl. the zero self edge (Processor.py:120):
  * out_host = {sum of lengths, edge count}; synchronises */
 int ngpd_session_mean_edge_length(ngpd_session_t* s, int k, double* out_host, void* stream);
+/* per-kernel device time, measured with CUDA events on the launching stream while profiling is on.
+ * Categories: 0 kNN, 1 NVT+smoothing, 2 NVT+labels, 3 flat-step scalars, 4 class updates.
+ * get_profile returns and clears the totals (ms_out[5], launches_out[5]); it waits for the recorded events. */
+int ngpd_session_set_profiling(ngpd_session_t* s, int on);
+int ngpd_session_get_profile(ngpd_session_t* s, double* ms_out, int32_t* launches_out);
 /* number of kernels the last ngpd_session_step launched */
 int ngpd_session_launch_count(const ngpd_session_t* s);
 /* tree-order views for tests/benchmarks: perm (sorted -> original) */

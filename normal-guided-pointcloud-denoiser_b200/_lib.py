@@ -57,6 +57,8 @@ SIGNATURES = {
     "ngpd_session_phase_commit_normals": (ctypes.c_int, [c_vp]),
     "ngpd_session_mean_edge_length": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_double), c_vp]),
     "ngpd_session_launch_count": (ctypes.c_int, [c_vp]),
+    "ngpd_session_set_profiling": (ctypes.c_int, [c_vp, ctypes.c_int]),
+    "ngpd_session_get_profile": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_i32)]),
     "ngpd_session_order": (ctypes.c_int, [c_vp, c_vp, c_vp]),
     "ngpd_session_buffer": (c_vp, [c_vp, ctypes.c_int]),
     "ngpd_session_export_rows": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_i64, c_vp, c_vp]),
@@ -234,6 +236,17 @@ class Session:
         with torch.cuda.device(self.device):
             check(load().ngpd_session_mean_edge_length(self._h, k, out, stream()), "ngpd_session_mean_edge_length")
         return out[0], out[1]
+
+    PROFILE_NAMES = ("knn", "nvt_smooth", "nvt_classify", "flat_scalars", "update")
+
+    def set_profiling(self, on: bool):
+        check(load().ngpd_session_set_profiling(self._h, int(on)), "ngpd_session_set_profiling")
+
+    def get_profile(self) -> dict:
+        ms = (ctypes.c_double * 5)()
+        cnt = (c_i32 * 5)()
+        check(load().ngpd_session_get_profile(self._h, ms, cnt), "ngpd_session_get_profile")
+        return {name: (ms[i], cnt[i]) for i, name in enumerate(self.PROFILE_NAMES)}
 
     def launch_count(self) -> int:
         return load().ngpd_session_launch_count(self._h)

@@ -13,6 +13,8 @@
 #include "point_math.cuh"
 #include "../../include/ngpd.h"
 
+#define NGPD_PROF_CATEGORIES 5   // 0 knn, 1 nvt+smooth, 2 nvt+classify, 3 flat scalars, 4 update
+
 struct ngpd_session {
     ngpd_grid* grid = nullptr;
     int64_t n = 0;
@@ -28,7 +30,25 @@ struct ngpd_session {
     double* acc = nullptr;    // 4 doubles
     float* cd = nullptr;      // centre xyz, delta
     int launches = 0;
+    // optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline numbers)
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev;      // pairs
+    std::vector<int> ev_cat;
+    double prof_ms[NGPD_PROF_CATEGORIES] = {0, 0, 0, 0, 0};
+    int prof_n[NGPD_PROF_CATEGORIES] = {0, 0, 0, 0, 0};
 };
+
+namespace ngpd {
+struct ProfScope {
+    ngpd_session* S; cudaStream_t st; int cat; cudaEvent_t a = nullptr, b = nullptr;
+    ProfScope(ngpd_session* S_, cudaStream_t st_, int cat_) : S(S_), st(st_), cat(cat_) {
+        if (S->profiling) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); }
+    }
+    ~ProfScope() {
+        if (S->profiling) { cudaEventRecord(b, st); S->ev.push_back(a); S->ev.push_back(b); S->ev_cat.push_back(cat); }
+    }
+};
+}
 
 namespace ngpd {
 
@@ -287,12 +307,14 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_phase_feature
         int rc = ensure_idx(S, kf);
         if (rc) return rc;
         S->idx_k = kf;
-        rc = run_knn(S, kf, S->idx, st);
+        { ProfScope ps(S, st, 0); rc = run_knn(S, kf, S->idx, st); }
         if (rc) return rc;
-        session_nvt_smooth_kernel<<<b, 128, 0, st>>>(pos, Quad4{S->nrm}, S->owned, S->idx, S->n, kf, p->x_thresh, p->tau, p->damp, S->fn);
+        { ProfScope ps(S, st, 1);
+          session_nvt_smooth_kernel<<<b, 128, 0, st>>>(pos, Quad4{S->nrm}, S->owned, S->idx, S->n, kf, p->x_thresh, p->tau, p->damp, S->fn); }
         S->launches += 2;
     } else {
-        session_nvt_classify_kernel<<<b, 128, 0, st>>>(pos, Quad4{S->fn}, S->owned, S->idx, S->n, kf, p->x_thresh, p->scale, S->label, S->edge);
+        { ProfScope ps(S, st, 2);
+          session_nvt_classify_kernel<<<b, 128, 0, st>>>(pos, Quad4{S->fn}, S->owned, S->idx, S->n, kf, p->x_thresh, p->scale, S->label, S->edge); }
         S->launches += 1;
     }
     NGPD_CUDA_OK(cudaGetLastError());
@@ -306,6 +328,7 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_phase_flat_sc
     cudaStream_t st = (cudaStream_t)stream_;
     NGPD_REQUIRE(S && p, "ngpd_session_phase_flat_scalars: NULL argument");
     Quad4 pos{S->pos[S->cur]};
+    ProfScope ps(S, st, 3);
     if (part == 0) {
         NGPD_CUDA_OK(cudaMemsetAsync(S->acc, 0, 4 * sizeof(double), st));
         session_class_sum_kernel<<<strided(S->n, 256), 256, 0, st>>>(pos, S->owned, S->label, key, S->idx, S->n, S->idx_k, p->k_update, S->acc);
@@ -324,6 +347,7 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_phase_update(
     NGPD_REQUIRE(S && p && key >= 0 && key < 3, "ngpd_session_phase_update: bad argument");
     int kind = p->strategy[key];
     if (kind < 0) return 0;
+    ProfScope ps(S, st, 4);
     session_update_kernel<<<(unsigned)cdiv(S->n, 128), 128, 0, st>>>(kind, key, Quad4{S->pos[S->cur]}, Quad4{S->fn}, S->edge, S->label, S->owned,
                                                                      S->idx, S->n, S->idx_k, p->k_update, p->alpha[key], p->dmax, S->cd,
                                                                      S->pos[S->cur ^ 1]);
@@ -373,6 +397,26 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_mean_edge_len
     NGPD_CUDA_OK(cudaFreeAsync(idx, st));
     NGPD_CUDA_OK(cudaFreeAsync(acc, st));
     out_host[0] = h[0]; out_host[1] = h[1];   // {sum of edge lengths, edge count}: callers divide (and all-reduce first on multi-GPU)
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int ngpd_session_set_profiling(ngpd_session_t* S, int on) {
+    NGPD_REQUIRE(S, "ngpd_session_set_profiling: NULL session");
+    S->profiling = on != 0;
+    return 0;
+}
+// accumulated device time per kernel category since the last call (synchronises the recorded events)
+extern "C" __attribute__((visibility("default"))) int ngpd_session_get_profile(ngpd_session_t* S, double* ms_out, int32_t* launches_out) {
+    NGPD_REQUIRE(S && ms_out && launches_out, "ngpd_session_get_profile: NULL argument");
+    for (size_t i = 0; i < S->ev_cat.size(); ++i) {
+        float ms = 0;
+        cudaEventSynchronize(S->ev[2 * i + 1]);
+        cudaEventElapsedTime(&ms, S->ev[2 * i], S->ev[2 * i + 1]);
+        S->prof_ms[S->ev_cat[i]] += ms; S->prof_n[S->ev_cat[i]] += 1;
+        cudaEventDestroy(S->ev[2 * i]); cudaEventDestroy(S->ev[2 * i + 1]);
+    }
+    S->ev.clear(); S->ev_cat.clear();
+    for (int c = 0; c < NGPD_PROF_CATEGORIES; ++c) { ms_out[c] = S->prof_ms[c]; launches_out[c] = S->prof_n[c]; S->prof_ms[c] = 0; S->prof_n[c] = 0; }
     return 0;
 }
 

@@ -1,0 +1,118 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/ngpd.h declares, the ctypes table
+matches it, compute calls refuse to run without a device, and the host-side logic of the Python mirror."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "ngpd.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ngpd_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as ge
+    ge.build()
+    import ngpd_b200
+    lib = ctypes.CDLL(ngpd_b200._lib.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in ngpd.h but not exported"
+    assert set(names) == set(ngpd_b200._lib.SIGNATURES), set(names) ^ set(ngpd_b200._lib.SIGNATURES)
+    assert lib.ngpd_version() == 100
+
+
+def test_no_cpu_fallback():
+    import ngpd_b200
+    from ngpd_b200 import _lib
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    pc = ngpd_b200.Pointcloud(torch.rand(10, 3))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ngpd_b200.Processor(pc)
+    with pytest.raises(RuntimeError):
+        _lib.Grid(torch.rand(10, 3))
+    with pytest.raises(RuntimeError):
+        ngpd_b200.TorchUtils.ChamferDistance(torch.rand(5, 3), torch.rand(5, 3))
+
+
+def test_selection_container():
+    from ngpd_b200 import Selection
+    j = torch.tensor([0, 1, 2, 1, 0, 2, 2, 1, 0])
+    s = Selection(torch.arange(3), j, torch.tensor([0, 3, 6, 9]))
+    assert len(s) == 3 and s.uniform_k() == 3
+    assert torch.equal(s[1], torch.tensor([1, 0, 2]))
+    assert torch.equal(s.getEdgeIndex(), torch.stack([torch.arange(3).repeat_interleave(3), j]))
+    f = s.filter(torch.tensor([2, 0]))
+    assert torch.equal(f.i, torch.tensor([2, 0])) and torch.equal(f.j, torch.tensor([2, 1, 0, 0, 1, 2]))
+    assert torch.equal(f.slices, torch.tensor([0, 3, 6]))
+    src = torch.arange(9, dtype=torch.float32)
+    assert torch.equal(s.scatter(src, "add"), torch.tensor([3.0, 12.0, 21.0]))
+    assert torch.equal(s.scatter(src, "mean"), torch.tensor([1.0, 4.0, 7.0]))
+    assert torch.equal(s.scatter(src, "max")[0], torch.tensor([2.0, 5.0, 8.0]))
+    ragged = Selection(torch.arange(2), torch.tensor([1, 0, 1]), torch.tensor([0, 1, 3]))
+    assert ragged.uniform_k() is None
+    with pytest.raises(AssertionError):
+        Selection(torch.arange(3), j.float(), torch.tensor([0, 3, 6, 9]))
+    with pytest.raises(AssertionError):
+        Selection(torch.arange(3), j, torch.tensor([1, 3, 6, 9]))
+
+
+def test_range_boundaries():
+    from ngpd_b200 import TorchUtils
+    got = TorchUtils.rangeBoundariesToIndices(torch.tensor([5, 0, 9]), torch.tensor([8, 2, 9]))
+    assert got.tolist() == [5, 6, 7, 0, 1]
+    assert TorchUtils.rangeBoundariesToIndices(torch.tensor([3]), torch.tensor([3])).numel() == 0
+
+
+def test_obj_roundtrip(tmp_path):
+    from ngpd_b200 import Pointcloud
+    v = torch.tensor([[0.0, 1.0, 2.0], [3.5, -4.25, 5.125], [1e-3, 2e5, -7.0]])
+    n = torch.nn.functional.normalize(torch.tensor([[0.0, 0.0, 1.0], [1.0, 1.0, 0.0], [0.0, -2.0, 0.0]]), dim=1)
+    p = tmp_path / "a.obj"
+    Pointcloud(v, n).saveObj(str(p))
+    back = Pointcloud.loadObj(str(p), device="cpu")
+    assert torch.equal(back.v, v) and torch.allclose(back.n, n)
+    with pytest.raises(FileExistsError):
+        Pointcloud(v).saveObj(str(p))
+    q = tmp_path / "mesh.obj"
+    q.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nv 1 1 0\nvn 0 0 1\nf 1//1 2//1 3//1\nf 2//1 4//1 3//1\n")
+    m = Pointcloud.loadObj(str(q), device="cpu")
+    assert m.v.shape == (4, 3) and torch.allclose(m.n, torch.tensor([[0.0, 0.0, 1.0]]).expand(4, 3))
+    with pytest.raises(AssertionError):
+        Pointcloud(torch.zeros(3, 2))
+    with pytest.raises(AssertionError):
+        Pointcloud.loadObj(str(tmp_path / "missing.obj"))
+
+
+def test_noise_validation_and_seeding():
+    from ngpd_b200.GraphBuilder import Graph
+    from ngpd_b200 import Noise
+    g = Graph(pos=torch.zeros(50, 3), n=torch.tensor([[0.0, 0.0, 1.0]]).repeat(50, 1))
+    nz = Noise(g)
+    with pytest.raises(ValueError):
+        nz.generateNoise(1.5, 1.0)
+    torch.manual_seed(5)
+    nz.generateNoise(0.3, 2.0, keepNormals=True)
+    a = g.pos.clone()
+    assert torch.equal(g.gt, torch.zeros(50, 3)) and (a[:, :2] == 0).all() and a[:, 2].std() > 0.2
+    nz.resetNoise()
+    torch.manual_seed(5)
+    nz.generateNoise(0.3, 2.0, keepNormals=True)
+    assert torch.equal(g.pos, a)
+
+
+def test_acos_threshold_matches_oracle():
+    import math
+    import ngpd_oracle as O
+    from ngpd_b200 import _lib
+    for rho in (math.pi * 5 / 12, 0.9, 0.95, math.pi * 23 / 48):
+        assert np.float32(_lib.acos_threshold(rho)) == O.acos_threshold(rho)

@@ -1,0 +1,449 @@
+"""GPU parity tests: the CUDA path (through the C ABI of libngpd.so and the Python mirror of the reference
+classes) against the oracle on the same inputs and against golden vectors recorded from the unmodified reference.
+Tolerances (north star): kNN indices and labels bit-exact; normals 1e-4 rad; positions 1e-5 relative; metrics 1e-6
+relative.  fp32 throughout, fp64 only inside the kNN distance."""
+import math
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import ngpd_oracle as O
+from conftest import angle_between
+
+pytestmark = pytest.mark.gpu
+RHO = math.pi * 5 / 12
+
+
+@pytest.fixture(scope="module")
+def ng():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import ngpd_b200
+    ngpd_b200._lib.load()
+    return ngpd_b200
+
+
+def cu(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return t if dtype is None else t.to(dtype)
+
+
+def surface_cloud(n, seed=0, noise=0.004):
+    """points on the unit cube's faces plus a torus around one edge: flat parts, creases, corners"""
+    rng = np.random.default_rng(seed)
+    nc = int(n * 0.6)
+    face = rng.integers(0, 6, nc)
+    uv = rng.uniform(-1, 1, (nc, 2))
+    cube = np.zeros((nc, 3))
+    for a in range(3):
+        m = face // 2 == a
+        o = [c for c in range(3) if c != a]
+        cube[m, a] = np.where(face[m] % 2 == 0, -1.0, 1.0)
+        cube[m, o[0]] = uv[m, 0]; cube[m, o[1]] = uv[m, 1]
+    nt = n - nc
+    u, v = rng.uniform(0, 2 * np.pi, nt), rng.uniform(0, 2 * np.pi, nt)
+    tor = np.stack([(0.6 + 0.25 * np.cos(v)) * np.cos(u) + 1.0, (0.6 + 0.25 * np.cos(v)) * np.sin(u) + 1.0, 0.25 * np.sin(v)], 1)
+    p = np.concatenate([cube, tor]) + rng.normal(0, noise, (n, 3))
+    return rng.permutation(p).astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------------
+# kNN
+# ------------------------------------------------------------------------------------------------------
+def test_knn_six_point_known_answer(ng):
+    v = np.array([[-0.03785068, 0.12783747, 0.00448816], [-0.044779, 0.128887, 0.001905], [-0.06801, 0.151244, 0.037195],
+                  [-0.070454, 0.150585, -0.043458], [-0.031026, 0.153728, -0.003546], [-0.040044, 0.15362, -0.008167]], dtype=np.float32)
+    want = np.array([[1, 4, 5], [0, 5, 4], [1, 0, 5], [5, 4, 1], [5, 0, 1], [4, 1, 0]])
+    g = ng._lib.Grid(cu(v), 4)
+    assert np.array_equal(g.knn(cu(v), 4).cpu().numpy()[:, 1:], want)                   # scipy form: drop the self column
+    assert np.array_equal(g.knn(cu(v), 3, ng._lib.KNN_SKIP_SELF).cpu().numpy(), want)  # torch_cluster form
+
+
+@pytest.mark.parametrize("k,key", [(6, "knn6"), (16, "it0_knn16"), (8, "it0_knn8"), (16, "it1_knn16"), (8, "it1_knn8")])
+def test_knn_fandisk_vs_reference(ng, fandisk, k, key):
+    tree = fandisk["pos0"]
+    query = fandisk["it1_pos_in"] if key.startswith("it1") else tree
+    got = ng._lib.Grid(cu(tree), k).knn(cu(query), k, ng._lib.KNN_QUERY_IS_TREE).cpu().numpy().astype(np.int64)
+    assert np.array_equal(got, O.knn_bruteforce(tree, query, k))                        # bit-exact vs the oracle's rule
+    assert O.tie_groups_equal(tree, query, got, fandisk[key].astype(np.int64))          # == SciPy up to exact ties
+
+
+def test_knn_graph_noself_fandisk(ng, fandisk):
+    tree = fandisk["pos0"]
+    got = ng._lib.Grid(cu(tree), 12).knn(cu(tree), 12, ng._lib.KNN_SKIP_SELF | ng._lib.KNN_QUERY_IS_TREE).cpu().numpy()
+    assert np.array_equal(got, O.knn_graph_noself(tree, 12))
+    assert O.tie_groups_equal(tree, tree, got.astype(np.int64), fandisk["knn12_noself"].astype(np.int64))
+
+
+@pytest.mark.parametrize("kind", ["volume", "surface", "lattice", "duplicates", "line", "clusters"])
+@pytest.mark.parametrize("k", [1, 7, 16, 32, 64])
+def test_knn_random_clouds_bit_exact(ng, kind, k):
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(f"{kind}{k}".encode()))
+    n = 3000
+    if kind == "volume":
+        tree = rng.uniform(-1, 1, (n, 3))
+    elif kind == "surface":
+        tree = surface_cloud(n, 5)
+    elif kind == "lattice":       # exact distance ties everywhere
+        ax = np.arange(15, dtype=np.float64)
+        tree = np.stack(np.meshgrid(ax, ax, ax, indexing="ij"), -1).reshape(-1, 3)[:n] * 0.25
+    elif kind == "duplicates":    # coincident points: ties at distance 0
+        base = rng.uniform(0, 1, (n // 4, 3))
+        tree = np.concatenate([base] * 4)
+    elif kind == "line":          # degenerate bbox (two zero extents)
+        tree = np.zeros((n, 3)); tree[:, 0] = rng.uniform(0, 5, n)
+    else:                         # very uneven density + outliers far from everything
+        tree = np.concatenate([rng.normal(0, 0.01, (n - 10, 3)), rng.uniform(50, 60, (10, 3))])
+    tree = tree.astype(np.float32)
+    query = np.concatenate([tree[rng.permutation(n)[:1500]] + rng.normal(0, 0.01, (1500, 3)).astype(np.float32),
+                            rng.uniform(-3, 3, (200, 3)).astype(np.float32)]).astype(np.float32)   # some far outside the bbox
+    g = ng._lib.Grid(cu(tree), k)
+    idx, d2 = g.knn(cu(query), k, 0, with_d2=True)
+    want = O.knn_bruteforce(tree, query, k)
+    assert np.array_equal(idx.cpu().numpy(), want)
+    ref_d2 = O.sqdist_rows_fp64(tree, query, want).astype(np.float32)
+    assert np.array_equal(d2.cpu().numpy(), ref_d2)
+
+
+def test_knn_fewer_points_than_k(ng):
+    tree = np.random.default_rng(1).uniform(0, 1, (5, 3)).astype(np.float32)
+    got = ng._lib.Grid(cu(tree), 8).knn(cu(tree), 8).cpu().numpy()
+    want = O.knn_bruteforce(tree, tree, 8)
+    assert np.array_equal(got, want) and (got[:, 5:] == 5).all()           # missing slots hold n, like SciPy
+    one = ng._lib.Grid(cu(tree[:1]), 1).knn(cu(tree), 1).cpu().numpy()
+    assert (one == 0).all()
+
+
+def test_knn_bad_arguments(ng):
+    tree = cu(np.zeros((4, 3), np.float32))
+    g = ng._lib.Grid(tree, 4)
+    with pytest.raises(ng._lib.NgpdError):
+        g.knn(tree, 65)
+    with pytest.raises(RuntimeError):
+        g.knn(torch.zeros(4, 3), 2)                                       # CPU tensor: no fallback
+    with pytest.raises(ng._lib.NgpdError):
+        ng._lib.Grid(cu(np.full((4, 3), np.nan, np.float32)), 4)
+
+
+def test_knn_large_properties(ng):
+    """2 M points: rows sorted, self first, and a sample of rows equal to SciPy's KD-tree."""
+    n, k = 2_000_000, 16
+    tree = surface_cloud(n, 11, noise=0.0005)
+    t = cu(tree)
+    g = ng._lib.Grid(t, k)
+    info = g.info()
+    assert info.n == n and 2.0 < n / info.occupied_cells < 20.0
+    idx, d2 = g.knn(t, k, ng._lib.KNN_QUERY_IS_TREE, with_d2=True)
+    assert bool((d2[:, 1:] >= d2[:, :-1]).all())
+    assert bool((idx[:, 0] == torch.arange(n, device="cuda")).float().mean() > 0.9999)   # coincident points may swap
+    assert bool((d2[:, 0] == 0).all())
+    rows = np.random.default_rng(0).permutation(n)[:3000]
+    want = O.knn_kdtree(tree, tree[rows], k)
+    got = idx[cu(rows)].cpu().numpy().astype(np.int64)
+    assert O.tie_groups_equal(tree, tree[rows], got, want)
+    perm = g.order().cpu().numpy()
+    assert np.array_equal(np.sort(perm), np.arange(n))
+
+
+# ------------------------------------------------------------------------------------------------------
+# neighbourhood operators, teacher-forced on the reference's inputs for each stage
+# ------------------------------------------------------------------------------------------------------
+def test_pca_normals(ng, fandisk):
+    pc = ng.Pointcloud(cu(fandisk["pos0"]))
+    p = ng.Processor(pc)
+    ei = p.graphBuilder.getKNNEdgeIndex(12)
+    assert ei.shape == (2, len(fandisk["pos0"]) * 12) and ei.dtype == torch.long
+    assert torch.equal(ei[0], torch.arange(len(fandisk["pos0"]), device="cuda").repeat_interleave(12))
+    p.graph.edge_index = cu(np.stack([np.repeat(np.arange(len(fandisk["pos0"])), 12), fandisk["knn12_noself"].reshape(-1)]), torch.long)
+    p.graphBuilder.setAndFlipNormals(flip=False)
+    assert angle_between(p.graph.n.cpu().numpy(), fandisk["n_pca"]).max() < 1e-4      # sign-consistent with LAPACK
+    vec = p.graphBuilder.getPVTDecompositionWithKNN(p.graph.edge_index)
+    assert angle_between(vec[:, :, 0].cpu().numpy(), fandisk["n_pca"]).max() < 1e-4
+    p.graphBuilder.flipNormals()
+    agree = ((p.graph.n.cpu().numpy() * fandisk["n_flip"]).sum(1) > 0).mean()
+    assert agree > 0.97, agree
+
+
+def _processor(ng, pos, nrm, tree=None):
+    pc = ng.Pointcloud(cu(tree if tree is not None else pos))
+    p = ng.Processor(pc)
+    p.graph.pos = cu(pos).clone()
+    p.graph.n = cu(nrm).clone()
+    return p
+
+
+@pytest.mark.parametrize("it", [0, 1])
+def test_nvt_smooth_classify_teacher_forced(ng, fandisk, it):
+    t = f"it{it}_"
+    p = _processor(ng, fandisk[t + "pos_in"], fandisk[t + "n_in"], tree=fandisk["pos0"])
+    sel = p.selector.getKNNSelection(16)
+    assert np.array_equal(sel.j.view(-1, 16).cpu().numpy(), O.knn_bruteforce(fandisk["pos0"], fandisk[t + "pos_in"], 16))
+    # run the tensor stage on the reference's own neighbour table (differs from ours only on exact-tie rows)
+    sel = ng.Selection(sel.i, cu(fandisk[t + "knn16"].reshape(-1), torch.long), sel.slices)
+    n = len(sel)
+    lib = ng._lib.load()
+    pos, nrm = p.graph.pos, p.graph.n
+    ev = torch.empty((n, 3), device="cuda"); vec = torch.empty((n, 3, 3), device="cuda"); T = torch.empty((n, 3, 3), device="cuda")
+    sw = torch.empty(n, dtype=torch.int32, device="cuda")
+    ng._lib.check(lib.ngpd_nvt(pos.data_ptr(), nrm.data_ptr(), sel.table().data_ptr(), None, None, n, 16, ng._lib.acos_threshold(RHO),
+                               ev.data_ptr(), vec.data_ptr(), T.data_ptr(), sw.data_ptr(), None), "nvt")
+    assert np.array_equal(T.cpu().numpy(), fandisk[t + "T1"])                         # voting tensors bit-exact
+    assert np.abs(ev.cpu().numpy() - fandisk[t + "eigval1"]).max() < 1e-6
+    dec = p.decompositionor.getBetterFilteredNVT(sel, nrm, RHO)
+    assert torch.equal(dec.eigval, ev) and torch.equal(dec.eigvec, vec)
+    gap = np.diff(fandisk[t + "eigval1"], axis=1).min(axis=1)
+    signs = ((vec.cpu().numpy() * fandisk[t + "eigvec1"]).sum(1) > 0).all(1)
+    assert signs[gap > 1e-2].all() and signs.mean() > 0.99                            # LAPACK's signs reproduced
+    # smoothing given the reference's eigen-decomposition
+    ref_dec = ng.Decomposition(cu(fandisk[t + "eigval1"]), cu(fandisk[t + "eigvec1"]))
+    f = ref_dec.getVUSmoothedNormals(nrm)
+    assert angle_between(f.cpu().numpy(), fandisk[t + "f_n"]).max() < 1e-4
+    assert np.array_equal(f.cpu().numpy(), fandisk[t + "f_n"])
+    # free-running smoothing: agreement at the reference's own noise floor
+    f_own = dec.getVUSmoothedNormals(nrm)
+    assert (angle_between(f_own.cpu().numpy(), fandisk[t + "f_n"]) > 1e-4).mean() < 0.0082
+    # stage 2 on the reference's smoothed normals -> labels
+    dec2 = p.decompositionor.getBetterFilteredNVT(sel, cu(fandisk[t + "f_n"]), RHO)
+    assert np.abs(dec2.eigval.cpu().numpy() - fandisk[t + "eigval2"]).max() < 1e-6
+    assert np.array_equal(dec2.getClasses().cpu().numpy(), fandisk[t + "classes"])    # labels bit-exact
+    pla, lin, sph = dec2.getNVTFeatures()
+    assert np.allclose(torch.stack([pla, lin, sph], 1).cpu().numpy(), fandisk[t + "features"], rtol=0, atol=2e-6)
+    assert torch.equal(dec2.getVUFeatures(0.3), (dec2.eigval < 0.3).sum(1) % 3)
+
+
+@pytest.mark.parametrize("it", [0, 1])
+def test_update_steps_teacher_forced(ng, fandisk, it):
+    t = f"it{it}_"
+    p = _processor(ng, fandisk[t + "pos_in"], fandisk[t + "n_in"], tree=fandisk["pos0"])
+    f = cu(fandisk[t + "f_n"]); cls = cu(fandisk[t + "classes"]).long()
+    edge = cu(np.ascontiguousarray(fandisk[t + "eigvec2"][:, :, 0]))
+    n = len(fandisk["pos0"])
+    sel8 = ng.Selection(torch.arange(n, device="cuda"), cu(fandisk[t + "knn8"].reshape(-1), torch.long), torch.arange(n + 1, device="cuda") * 8)
+    d = float(np.float32(2) * fandisk["l"])
+    scale = np.abs(fandisk[t + "pos_in"]).max()
+    for key, alpha in ((0, 1), (1, 0.2), (2, 1)):
+        rows = (cls == key).nonzero().flatten()
+        sub = sel8.filter(rows)
+        if key == 0:
+            new = p.denoiser.flat_step(sub, f, d, alpha)
+        elif key == 1:
+            new = p.denoiser.edge_step(sub, f, edge, d, alpha)
+        else:
+            new = p.denoiser.feature_step(sub, f, d, alpha)
+        ref = fandisk[t + f"pos_after_class{key}"]
+        assert np.abs(new.cpu().numpy() - ref[rows.cpu().numpy()]).max() / scale < 1e-5, key
+        p.graph.pos = cu(ref).clone(); p.denoiser.graph = p.graph
+    # the remaining step kinds on all points (recorded after iteration 0's class loop)
+    if it == 0:
+        allsel = sel8
+        feat = p.denoiser.feature_step(allsel, f, d, 0.5)
+        assert np.abs(feat.cpu().numpy() - fandisk["feature_all"]).max() / scale < 1e-5
+        cor = p.denoiser.corner_step(allsel, f, d, 0.1).cpu().numpy()
+        nj = fandisk[t + "f_n"][fandisk[t + "knn8"]]
+        ok = O.solve_condition(np.einsum("nki,nkj->nij", nj, nj)) < 1e3
+        assert np.abs(cor - fandisk["corner_all"])[ok].max() / scale < 1e-5
+        assert torch.equal(p.denoiser.dummy_step(allsel, f, d), p.graph.pos)
+
+
+def test_ragged_selection_rows(ng, fandisk):
+    """CSR rows of different length (what a radius selection produces) go through the same kernels."""
+    pos, nrm = fandisk["it0_pos_in"], fandisk["it0_n_in"]
+    p = _processor(ng, pos, nrm)
+    n = 500
+    rng = np.random.default_rng(2)
+    lens = rng.integers(3, 17, n)
+    full = fandisk["it0_knn16"][:n]
+    j = np.concatenate([full[r, :lens[r]] for r in range(n)])
+    slices = np.concatenate([[0], np.cumsum(lens)])
+    sel = ng.Selection(torch.arange(n, device="cuda"), cu(j, torch.long), cu(slices, torch.long))
+    dec = p.decompositionor.getBetterFilteredNVT(sel, p.graph.n, RHO)
+    xt = O.acos_threshold(RHO)
+    for r in (0, 17, 499):
+        w, V, T, _ = O.nvt(pos, nrm, np.array([r]), full[r:r + 1, :lens[r]], xt)
+        assert np.abs(dec.eigval[r].cpu().numpy() - w[0]).max() < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------------
+# metrics
+# ------------------------------------------------------------------------------------------------------
+def test_metrics_vs_reference(ng, fandisk):
+    gt, pos = cu(fandisk["gt"]), cu(fandisk["pos_final"])
+    T = ng.TorchUtils
+    cd = T.ChamferDistance(gt, pos).cpu().numpy()
+    ref = fandisk["cd_final"]
+    assert cd.shape == ref.shape
+    assert abs(cd.mean(dtype=np.float64) - ref.mean(dtype=np.float64)) / ref.mean(dtype=np.float64) < 1e-6
+    assert np.allclose(cd, ref, rtol=1e-5, atol=1e-9)
+    assert np.allclose(T.PaperDistance(gt, pos).cpu().numpy(), fandisk["paper_final"], rtol=1e-5, atol=1e-9)
+    assert np.allclose(T.HausdorffDistance(gt, pos).cpu().numpy(), fandisk["hausdorff_final"], rtol=1e-5, atol=1e-7)
+    assert np.array_equal(T.SingleChamferDistance(gt, pos).cpu().numpy(), cd[:len(fandisk["pos_final"])])
+    assert abs(float(T.pointcloudRadius(pos)) - float(fandisk["radius_final"])) / float(fandisk["radius_final"]) < 1e-6
+    cd0 = T.ChamferDistance(gt, cu(fandisk["pos0"])).cpu().numpy()
+    assert abs(cd0.mean(dtype=np.float64) - fandisk["cd_initial"].mean(dtype=np.float64)) / fandisk["cd_initial"].mean(dtype=np.float64) < 1e-6
+
+
+def test_chamfer_properties_large(ng):
+    a = cu(surface_cloud(1_000_000, 3))
+    T = ng.TorchUtils
+    assert float(T.ChamferDistance(a, a).abs().max()) == 0.0                 # identity
+    shift = a + torch.tensor([0.0, 0.0, 5.0], device="cuda")
+    cd = T.ChamferDistance(a, shift)
+    assert float(cd.min()) >= 0 and cd.numel() == 2 * a.size(0)
+    b = a[torch.randperm(a.size(0), device="cuda")[:200_000]]
+    one = T.ChamferDistance(a, b)
+    assert float(one[:b.size(0)].max()) == 0.0                               # subset -> superset distances vanish
+    m1, m2 = float(T.ChamferDistance(a, b).double().mean()), float(T.ChamferDistance(b, a).double().mean())
+    assert abs(m1 - m2) / m1 < 1e-9                                          # mean over the concatenation is symmetric
+
+
+# ------------------------------------------------------------------------------------------------------
+# the loops
+# ------------------------------------------------------------------------------------------------------
+def _fandisk_processor(ng, fandisk):
+    p = ng.Processor(ng.Pointcloud(cu(fandisk["pos0"]).clone()))
+    p.graph.n = cu(fandisk["n_flip"]).clone()
+    return p
+
+
+def test_denoise_fused_equals_unfused(ng, fandisk):
+    a = _fandisk_processor(ng, fandisk); a.denoise()
+    b = _fandisk_processor(ng, fandisk); b.denoise_unfused()
+    scale = float(a.graph.pos.abs().max())
+    assert float((a.graph.pos - b.graph.pos).abs().max()) / scale < 2e-6
+    assert angle_between(a.graph.n.cpu().numpy(), b.graph.n.cpu().numpy()).max() < 1e-4
+
+
+def test_denoise_vs_reference_free_running(ng, fandisk):
+    """Processor.denoise() end to end against the reference's result.  The reference's smoothing depends on LAPACK's
+    eigenvector signs inside rank-deficient tensors (a 1-ulp change of its own input moves 0.82 % of its normals by
+    > 1e-4 rad and flips 10/6475 labels: SURVEY.md 8a row 5), so the free-running comparison is statistical, held to
+    that noise floor; the stage-wise tests above carry the strict tolerances."""
+    p = _fandisk_processor(ng, fandisk)
+    pos_before = p.graph.pos
+    p.denoise()
+    assert p.graph.pos is pos_before                                          # updated in place, like the reference
+    pos, nrm = p.graph.pos.cpu().numpy(), p.graph.n.cpu().numpy()
+    scale = np.abs(fandisk["pos_final"]).max()
+    err = np.abs(pos - fandisk["pos_final"]).max(axis=1) / scale
+    ang = angle_between(nrm, fandisk["n_final"])
+    print(f"\nfree-running denoise(): positions >1e-5: {(err > 1e-5).mean():.4%} (max {err.max():.2e}); normals >1e-4 rad: {(ang > 1e-4).mean():.4%}")
+    assert (err > 1e-5).mean() < 0.02
+    assert (ang > 1e-4).mean() < 0.02
+    cd = ng.TorchUtils.ChamferDistance(cu(fandisk["gt"]), p.graph.pos).double().mean().item()
+    ref = fandisk["cd_final"].mean(dtype=np.float64)
+    assert abs(cd - ref) / ref < 1e-3
+
+
+def test_session_labels_vs_reference(ng, fandisk):
+    """Labels of iteration 0 from the fused session (own kNN, own eigen-solver) vs the reference."""
+    sess = ng._lib.Session(cu(fandisk["pos0"]), 16)
+    sess.set_state(cu(fandisk["pos0"]), cu(fandisk["n_flip"]))
+    d = float(np.float32(2) * fandisk["l"])
+    s, c = sess.mean_edge_length_parts(6)
+    assert abs(s / c - float(fandisk["l"])) / float(fandisk["l"]) < 1e-6
+    sess.step(ng._lib.make_params(dmax=d))
+    pos, fn, lab = sess.get_state(True)
+    agree = (lab.cpu().numpy() == fandisk["it0_classes"]).mean()
+    print(f"\nfree-running labels agree with the reference on {agree:.4%} of points")
+    assert agree > 0.995
+    assert (angle_between(fn.cpu().numpy(), fandisk["it0_f_n"]) > 1e-4).mean() < 0.0082
+    err = np.abs(pos.cpu().numpy() - fandisk["it0_pos_after_class2"]).max(axis=1) / np.abs(fandisk["pos0"]).max()
+    assert (err > 1e-5).mean() < 0.01
+    assert 8 <= sess.launch_count() <= 12
+
+
+def test_until_minimum_error_loop(ng, until_min):
+    """BASELINE config 2 on the recorded cloud: same stopping iteration and Chamfer history as the reference."""
+    p = ng.Processor(ng.Pointcloud(cu(until_min["pos0"]).clone()))
+    p.graph.n = cu(until_min["n_flip"]).clone()
+    l = float(until_min["l"])
+    hist = []
+
+    def cd(a, b):
+        r = ng.TorchUtils.ChamferDistance(a, b)
+        hist.append(float(r.double().mean()))
+        return r
+
+    strategy = {0: p.denoiser.flat_step, 1: p.denoiser.feature_step, 2: p.denoiser.feature_step}
+    noisy = p.graph.pos.clone()
+    best, prev_err, iters = p.denoiseUntilMinimumError(cu(until_min["gt"]), strategy, k=8, alpha=[1, 0.2, 1], d=2 * l, error_funcs=[cd])
+    ref_hist = until_min["cd_history"]
+    print("\nCD history ours", hist, "\nCD history ref ", ref_hist.tolist())
+    assert iters == int(until_min["iterations"])
+    assert len(hist) == len(ref_hist)
+    assert np.allclose(hist[:2], ref_hist[:2], rtol=1e-6)
+    assert np.allclose(hist, ref_hist, rtol=2e-3)
+    assert torch.equal(p.graph.pos, noisy)                                   # reset to the noisy input on exit
+    scale = np.abs(until_min["pos0"]).max()
+    err = np.abs(best.cpu().numpy() - until_min["pos_returned"]).max(axis=1) / scale
+    assert (err > 1e-5).mean() < 0.02
+
+
+def test_generic_strategy_path(ng, fandisk):
+    """A strategy holding a user callable falls back to the operator-by-operator loop."""
+    p = _fandisk_processor(ng, fandisk)
+    calls = []
+
+    def my_step(selection, n, d, alpha):
+        calls.append(len(selection))
+        return p.denoiser.feature_step(selection, n, d, alpha)
+
+    gt = cu(fandisk["gt"])
+    strategy = {0: p.denoiser.flat_step, 1: my_step, 2: p.denoiser.dummy_step}
+    best, err, it = p.denoiseUntilMinimumError(gt, strategy, k=8, alpha=[1, 0.2, 1], d=float(2 * fandisk["l"]),
+                                              error_funcs=[ng.TorchUtils.ChamferDistance])
+    assert calls and it >= 0
+
+
+def test_cube_labels_vs_reference(ng, cube):
+    p = ng.Processor(ng.Pointcloud(cu(cube["pos_clean"])))
+    p.graph.pos = cu(cube["pos"]).clone(); p.graph.n = cu(cube["n_flip"]).clone()
+    p.decompositionor.graph = p.graph; p.selector.graph = p.graph
+    sel = p.selector.getKNNSelection(16)
+    assert O.tie_groups_equal(cube["pos_clean"], cube["pos"], sel.j.view(-1, 16).cpu().numpy(), cube["knn16"].astype(np.int64))
+    sel = ng.Selection(sel.i, cu(cube["knn16"].reshape(-1), torch.long), sel.slices)       # reference's tie order
+    ang = float(cube["angle"])
+    nvt = p.decompositionor.getBetterFilteredNVT(sel, p.graph.n, ang)
+    f = nvt.getVUSmoothedNormals(p.graph.n)
+    dec = p.decompositionor.getBetterFilteredNVT(sel, f, ang)
+    agree = (dec.getClasses().cpu().numpy() == cube["classes"]).mean()
+    assert agree > 0.97, agree
+    # FeatureFix.ipynb#c1 rule: label = (#coordinates with |x| = 1) - 1; the reference scores 91.7 % on this cloud
+    assert (dec.getClasses().cpu().numpy() == cube["gt_label"]).mean() > 0.88
+
+
+def test_preprocess_pointcloud(ng, fandisk):
+    torch.manual_seed(0)
+    p = ng.Processor(ng.Pointcloud(cu(fandisk["gt"]).clone()))
+    p.preprocessPointcloud(k=12, noise_level=0.3)
+    g = p.graph
+    assert torch.equal(g.gt, cu(fandisk["gt"])) and g.n.shape == g.pos.shape
+    disp = (g.pos - g.gt).norm(dim=1)
+    l = float(ng.TorchUtils.averageEdgeLength(g.gt, g.edge_index))
+    assert 0.2 * l < float(disp.std()) < 0.5 * l                                # sigma = 0.3 * mean edge length along the normal
+    assert torch.allclose(g.n.norm(dim=1), torch.ones(g.num_nodes, device="cuda"), atol=1e-5)
+    # selector stays frozen on the clean cloud
+    assert torch.equal(p.selector.tree_pos, cu(fandisk["gt"]))
+
+
+def test_session_large_runs_and_is_deterministic(ng):
+    n = 1_000_000
+    cloud = cu(surface_cloud(n, 21, noise=0.001))
+    nrm = torch.nn.functional.normalize(torch.randn(n, 3, device="cuda"), dim=1)
+    outs = []
+    for _ in range(2):
+        sess = ng._lib.Session(cloud, 16)
+        sess.set_state(cloud, nrm)
+        s, c = sess.mean_edge_length_parts(6)
+        params = ng._lib.make_params(dmax=2 * s / c)
+        sess.step(params); sess.step(params)
+        outs.append(sess.get_state(True))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)                                              # no atomics in any per-point result
+    pos, fn, lab = outs[0]
+    assert torch.isfinite(pos).all() and torch.isfinite(fn).all()
+    assert torch.allclose(fn.norm(dim=1), torch.ones(n, device="cuda"), atol=1e-4)
+    assert int(lab.max()) <= 2
