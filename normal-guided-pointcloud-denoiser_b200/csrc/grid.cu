@@ -34,14 +34,17 @@ static inline float ordered_float(int i) {
 
 __global__ void __launch_bounds__(256) bbox_kernel(const float* __restrict__ pos, int64_t n, int* __restrict__ out6) {
     float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    bool bad = false;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             float v = __ldg(pos + 3 * i + c);
+            bad |= !isfinite(v);
             lo[c] = fminf(lo[c], v);
             hi[c] = fmaxf(hi[c], v);
         }
     }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(out6 + 6, 1);
 #pragma unroll
     for (int c = 0; c < 3; ++c)
 #pragma unroll
@@ -411,16 +414,17 @@ extern "C" __attribute__((visibility("default"))) int ngpd_grid_create(const flo
     G->n = n;
     // bounding box
     int* bb_d = nullptr;
-    NGPD_CUDA_OK(cudaMalloc(&bb_d, 6 * sizeof(int)));
-    int init[6] = {0x7f7fffff, 0x7f7fffff, 0x7f7fffff, (int)0x80800000, (int)0x80800000, (int)0x80800000};
+    NGPD_CUDA_OK(cudaMalloc(&bb_d, 7 * sizeof(int)));
+    int init[7] = {0x7f7fffff, 0x7f7fffff, 0x7f7fffff, (int)0x80800000, (int)0x80800000, (int)0x80800000, 0};
     for (int c = 3; c < 6; ++c) { float f = -FLT_MAX; int i; memcpy(&i, &f, 4); init[c] = i >= 0 ? i : i ^ 0x7fffffff; }
     NGPD_CUDA_OK(cudaMemcpyAsync(bb_d, init, sizeof(init), cudaMemcpyHostToDevice, stream));
     int blocks = (int)std::min<int64_t>(cdiv(n, 256), (int64_t)num_sms() * 8);
     bbox_kernel<<<blocks, 256, 0, stream>>>(pos, n, bb_d);
-    int bb_h[6];
+    int bb_h[7];
     NGPD_CUDA_OK(cudaMemcpyAsync(bb_h, bb_d, sizeof(bb_h), cudaMemcpyDeviceToHost, stream));
     NGPD_CUDA_OK(cudaStreamSynchronize(stream));
     cudaFree(bb_d);
+    if (bb_h[6]) { delete G; set_error("ngpd_grid_create: non-finite coordinates"); return -1; }
     for (int c = 0; c < 6; ++c) G->bbox[c] = ordered_float(bb_h[c]);
     for (int c = 0; c < 6; ++c)
         if (!std::isfinite(G->bbox[c])) { delete G; set_error("ngpd_grid_create: non-finite coordinates"); return -1; }

@@ -1,0 +1,145 @@
+"""Host-side logic of the multi-GPU path (Morton slabs, halo membership, request wiring, halo refresh, scalar
+all-reduces) exercised with world_size = 2 over gloo on CPU.  The per-point kernels are not involved: values are
+synthetic functions of the point id, and neighbourhoods come from the oracle."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _cloud(n=12000, seed=4):
+    rng = np.random.default_rng(seed)
+    u, v = rng.uniform(0, 2 * np.pi, n), rng.uniform(0, 2 * np.pi, n)
+    p = np.stack([(0.6 + 0.25 * np.cos(v)) * np.cos(u), (0.6 + 0.25 * np.cos(v)) * np.sin(u), 0.25 * np.sin(v)], 1)
+    return (p + rng.normal(0, 0.002, p.shape)).astype(np.float32)
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import ngpd_oracle as O
+        from ngpd_b200 import partition
+        pos_np = _cloud()
+        pos = torch.from_numpy(pos_np)
+        n = len(pos_np)
+        k = 16
+        hw = partition.estimate_halo_width(pos, k, factor=3.0)
+        plan = partition.SlabPlan(pos, rank, world, hw)
+        ex = partition.HaloExchanger(plan)
+
+        # 1. slabs partition the cloud, equal sizes
+        owned = [None] * world
+        dist.all_gather_object(owned, plan.owned.tolist())
+        flat = np.concatenate([np.asarray(o) for o in owned])
+        assert len(flat) == n and len(np.unique(flat)) == n
+        assert max(len(o) for o in owned) - min(len(o) for o in owned) <= 1
+        assert bool((plan.slab_of[plan.owned] == rank).all()) and bool((plan.slab_of[plan.halo] != rank).all())
+
+        # 2. the halo holds every foreign point a moved owned query can reach: move each point by up to 2 spacings and
+        #    check its exact 16-NN (oracle, full cloud) lies inside owned + halo
+        rng = np.random.default_rng(rank)
+        spacing = hw / (3.0 * np.sqrt(k / np.pi))
+        moved = pos_np[plan.owned.numpy()] + rng.normal(0, 0.5 * spacing, (plan.n_owned, 3)).astype(np.float32)
+        nn = O.knn_bruteforce(pos_np, moved, k)
+        local = np.zeros(n, dtype=bool)
+        local[plan.local_ids.numpy()] = True
+        assert local[nn].all(), "halo too thin"
+        assert plan.n_halo < 0.5 * n                                        # and it is a boundary layer, not the whole cloud
+
+        # 3. halo refresh: values that are a function of the original id arrive in the right rows
+        def values(ids, phase):
+            return torch.stack([ids.float() * (phase + 1), ids.float() + 0.25, -ids.float(), torch.full_like(ids, phase).float()], 1)
+
+        state = torch.zeros((plan.local_ids.numel(), 4))
+        for phase in range(3):
+            state[:plan.n_owned] = values(plan.owned, phase)
+            send = torch.cat([state[r] for r in ex.send_local])
+            recv = torch.empty((sum(ex.recv_counts), 4))
+            ex.exchange(send, recv)
+            state[torch.cat(ex.recv_local)] = recv
+            assert torch.equal(state, values(plan.local_ids, phase)), f"phase {phase}"
+        sb, rb = ex.bytes_per_exchange()
+        assert sb == sum(ex.send_counts) * 16 and rb == plan.n_halo * 16
+
+        # 4. flat_step's cloud-wide scalars from per-rank partial sums (sum, then max): same as the global ones
+        vj = pos[plan.owned].double()
+        acc = torch.cat([vj.sum(0), torch.tensor([float(plan.n_owned)], dtype=torch.float64)])
+        dist.all_reduce(acc)
+        centre = (acc[:3] / acc[3]).float()
+        delta = (pos[plan.owned] - centre).norm(dim=1).max()
+        dist.all_reduce(delta, op=dist.ReduceOp.MAX)
+        gc = pos.double().mean(0).float()
+        assert torch.allclose(centre, gc, atol=1e-6) and abs(float(delta) - float((pos - gc).norm(dim=1).max())) < 1e-6
+
+        # 5. a distributed neighbourhood average over two phases equals the single-process result
+        nbr_full = O.knn_bruteforce(pos_np, pos_np, 8)
+        val = np.sin(np.arange(n, dtype=np.float64))
+        ref = val.copy()
+        for _ in range(2):
+            ref = ref[nbr_full].mean(1)
+        look = np.full(n, -1); look[plan.local_ids.numpy()] = np.arange(plan.local_ids.numel())
+        nbr_local = look[nbr_full[plan.owned.numpy()]]
+        assert (nbr_local >= 0).all()
+        st = torch.zeros((plan.local_ids.numel(), 4), dtype=torch.float64)
+        st[:, 0] = torch.from_numpy(val[plan.local_ids.numpy()])
+        for _ in range(2):
+            new = st[:, 0].numpy()[nbr_local].mean(1)
+            st[:plan.n_owned, 0] = torch.from_numpy(new)
+            send = torch.cat([st[r] for r in ex.send_local]); recv = torch.empty((sum(ex.recv_counts), 4), dtype=torch.float64)
+            ex.exchange(send, recv)
+            st[torch.cat(ex.recv_local)] = recv
+        assert np.allclose(st[:plan.n_owned, 0].numpy(), ref[plan.owned.numpy()], rtol=0, atol=1e-15)
+        out[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+def test_slab_plan_and_halo_exchange_world2():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert dict(out) == {0: "ok", 1: "ok"}
+
+
+def test_slab_plan_single_rank_has_no_halo():
+    sys.path.insert(0, ROOT)
+    from ngpd_b200 import partition
+    pos = torch.from_numpy(_cloud(2000))
+    plan = partition.SlabPlan(pos, 0, 1, partition.estimate_halo_width(pos, 16))
+    assert plan.n_owned == 2000 and plan.n_halo == 0
+    assert torch.equal(torch.sort(plan.owned).values, torch.arange(2000))
+
+
+def test_morton_keys_order_is_spatial():
+    sys.path.insert(0, ROOT)
+    from ngpd_b200 import partition
+    pos = torch.rand(20000, 3)
+    keys = partition.morton_keys(pos, pos.min(0).values, pos.max(0).values)
+    # the leading bit of the code is the leading bit of the quantised z coordinate
+    zq = ((pos[:, 2] - pos[:, 2].min()) / (pos.max(0).values - pos.min(0).values).max() * (2 ** 21 - 1)).floor().long()
+    assert torch.equal(keys >> 62, zq >> 20)
+    # points sharing a long key prefix are close: consecutive points along the curve are near each other on average
+    order = torch.argsort(keys)
+    step = (pos[order[1:]] - pos[order[:-1]]).norm(dim=1).mean()
+    rand = (pos[1:] - pos[:-1]).norm(dim=1).mean()
+    assert float(step) < 0.15 * float(rand)
