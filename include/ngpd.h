@@ -57,6 +57,7 @@ int ngpd_grid_order(const ngpd_grid_t* grid, int32_t* perm_out, void* stream);
 #define NGPD_KNN_SKIP_SELF 1        /* query i IS tree point i: leave it out of its own row */
 #define NGPD_KNN_QUERY_IS_TREE 2    /* query i is the (possibly moved) tree point i: visit queries in tree order */
 #define NGPD_KNN_COHERENT 4         /* queries are already in a spatially coherent order: skip the ordering pass */
+#define NGPD_KNN_EXACT_ONLY 8       /* skip the warp-lockstep fast path: every query through the exact shell search (tests) */
 int ngpd_knn(const ngpd_grid_t* grid, const float* query, int64_t m, int k, int flags,
              int32_t* idx_out, float* d2_out, void* stream);
 
@@ -135,6 +136,10 @@ int ngpd_session_mean_edge_length(ngpd_session_t* s, int k, double* out_host, vo
  * get_profile returns and clears the totals (ms_out[5], launches_out[5]); it waits for the recorded events. */
 int ngpd_session_set_profiling(ngpd_session_t* s, int on);
 int ngpd_session_get_profile(ngpd_session_t* s, double* ms_out, int32_t* launches_out);
+/* kNN mode of the session: 0 = warp-lockstep fast path + exact fix-up (default), 1 = exact shell search for every
+ * query.  Both give the same rows.  last_fixups = queries the last kNN pass handed to the exact search (synchronises). */
+int ngpd_session_set_knn_mode(ngpd_session_t* s, int mode);
+int ngpd_session_last_fixups(ngpd_session_t* s, void* stream);
 /* number of kernels the last ngpd_session_step launched */
 int ngpd_session_launch_count(const ngpd_session_t* s);
 /* tree-order views for tests/benchmarks: perm (sorted -> original) */

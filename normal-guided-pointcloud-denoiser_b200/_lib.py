@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libngpd.so")
 
 c_i64, c_i32, c_f32, c_vp = ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_void_p
 
-KNN_SKIP_SELF, KNN_QUERY_IS_TREE, KNN_COHERENT = 1, 2, 4
+KNN_SKIP_SELF, KNN_QUERY_IS_TREE, KNN_COHERENT, KNN_EXACT_ONLY = 1, 2, 4, 8
 STEP_FLAT, STEP_EDGE, STEP_FEATURE, STEP_CORNER, STEP_NONE = 0, 1, 2, 3, -1
 
 
@@ -57,6 +57,8 @@ SIGNATURES = {
     "ngpd_session_phase_commit_normals": (ctypes.c_int, [c_vp]),
     "ngpd_session_mean_edge_length": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_double), c_vp]),
     "ngpd_session_launch_count": (ctypes.c_int, [c_vp]),
+    "ngpd_session_set_knn_mode": (ctypes.c_int, [c_vp, ctypes.c_int]),
+    "ngpd_session_last_fixups": (ctypes.c_int, [c_vp, c_vp]),
     "ngpd_session_set_profiling": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "ngpd_session_get_profile": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_i32)]),
     "ngpd_session_order": (ctypes.c_int, [c_vp, c_vp, c_vp]),
@@ -247,6 +249,12 @@ class Session:
         cnt = (c_i32 * 5)()
         check(load().ngpd_session_get_profile(self._h, ms, cnt), "ngpd_session_get_profile")
         return {name: (ms[i], cnt[i]) for i, name in enumerate(self.PROFILE_NAMES)}
+
+    def set_knn_mode(self, exact_only: bool):
+        check(load().ngpd_session_set_knn_mode(self._h, 1 if exact_only else 0), "ngpd_session_set_knn_mode")
+
+    def last_fixups(self) -> int:
+        return load().ngpd_session_last_fixups(self._h, stream())
 
     def launch_count(self) -> int:
         return load().ngpd_session_launch_count(self._h)

@@ -1,4 +1,5 @@
-#include "knn.cuh"
+#include <algorithm>
+#include "knn_fast.cuh"
 #include "../../include/ngpd.h"
 
 namespace ngpd {
@@ -23,6 +24,59 @@ __global__ void __launch_bounds__(128) knn_kernel(GridView g, const float* __res
             row[a] = j >= 0 ? __float_as_int(__ldg(&g.pts[j].w)) : g.n;
             if (d2_out) d2_out[qi * k + a] = j >= 0 ? (float)top.d[a] : INFINITY;
         }
+    }
+}
+
+// fast path: warp-lockstep search (knn_fast.cuh); queries it cannot settle go to `fix_list`
+template <int K>
+__global__ void __launch_bounds__(KF_THREADS) knn_fast_kernel(GridView g, const float* __restrict__ query, const int32_t* __restrict__ qorder,
+                                                              int64_t m, int k, int skip_self, int32_t* __restrict__ idx_out,
+                                                              float* __restrict__ d2_out, int32_t* __restrict__ fix_list,
+                                                              int32_t* __restrict__ fix_count) {
+    __shared__ KfShared sm;
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool active = t < m;
+    int64_t qi = active ? (qorder ? (int64_t)qorder[t] : t) : 0;
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    if (active) { qx = __ldg(query + 3 * qi); qy = __ldg(query + 3 * qi + 1); qz = __ldg(query + 3 * qi + 2); }
+    Near<K> top;
+    top.init();
+    bool ok = knn_lockstep<K>(top, sm, g, qx, qy, qz, active, skip_self ? (int)qi : -1);
+    double ex[K];
+    near_finalize<K>(top, g.pts, qx, qy, qz, ex);
+    if (active && ok) {
+        int32_t* row = idx_out + qi * k;
+#pragma unroll
+        for (int a = 0; a < K; ++a)
+            if (a < k) {
+                row[a] = __float_as_int(top.d[a]);
+                if (d2_out) d2_out[qi * k + a] = (float)ex[a];
+            }
+    }
+    fix_append(active && !ok, (int)t, fix_list, fix_count);
+}
+
+// exact shell search for the listed queries
+template <int K>
+__global__ void __launch_bounds__(128) knn_fix_kernel(GridView g, const float* __restrict__ query, const int32_t* __restrict__ qorder,
+                                                      int k, int skip_self, int32_t* __restrict__ idx_out, float* __restrict__ d2_out,
+                                                      const int32_t* __restrict__ fix_list, const int32_t* __restrict__ fix_count) {
+    const int cnt = *fix_count;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+        int64_t t = fix_list[i];
+        int64_t qi = qorder ? (int64_t)qorder[t] : t;
+        double qx = (double)__ldg(query + 3 * qi), qy = (double)__ldg(query + 3 * qi + 1), qz = (double)__ldg(query + 3 * qi + 2);
+        TopK<K> top;
+        top.init();
+        knn_search<K>(top, g, qx, qy, qz, skip_self ? (int)qi : -1);
+        int32_t* row = idx_out + qi * k;
+#pragma unroll
+        for (int a = 0; a < K; ++a)
+            if (a < k) {
+                int j = top.id[a];
+                row[a] = j >= 0 ? __float_as_int(__ldg(&g.pts[j].w)) : g.n;
+                if (d2_out) d2_out[qi * k + a] = j >= 0 ? (float)top.d[a] : INFINITY;
+            }
     }
 }
 
@@ -83,6 +137,20 @@ static void launch_knn(const ngpd_grid* G, const float* query, const int32_t* or
     knn_kernel<K><<<(unsigned)cdiv(m, 128), 128, 0, s>>>(G->v, query, order, m, k, skip, idx, d2);
 }
 
+template <int K>
+static int launch_knn_fast(const ngpd_grid* G, const float* query, const int32_t* order, int64_t m, int k, int skip, int32_t* idx, float* d2,
+                           cudaStream_t s) {
+    int32_t* fix = nullptr;
+    NGPD_CUDA_OK(cudaMallocAsync(&fix, (size_t)(m + 1) * sizeof(int32_t), s));
+    NGPD_CUDA_OK(cudaMemsetAsync(fix + m, 0, sizeof(int32_t), s));
+    knn_fast_kernel<K><<<(unsigned)cdiv(m, KF_THREADS), KF_THREADS, 0, s>>>(G->v, query, order, m, k, skip, idx, d2, fix, fix + m);
+    int blocks = (int)std::min<int64_t>(cdiv(m, 128), (int64_t)num_sms() * 8);
+    knn_fix_kernel<K><<<blocks, 128, 0, s>>>(G->v, query, order, k, skip, idx, d2, fix, fix + m);
+    NGPD_CUDA_OK(cudaGetLastError());
+    NGPD_CUDA_OK(cudaFreeAsync(fix, s));
+    return 0;
+}
+
 }  // namespace ngpd
 
 using namespace ngpd;
@@ -97,12 +165,14 @@ extern "C" __attribute__((visibility("default"))) int ngpd_knn(const ngpd_grid_t
     int rc = make_query_order(G, query, m, flags, stream, &order);
     if (rc) return rc;
     int skip = (flags & NGPD_KNN_SKIP_SELF) ? 1 : 0;
+    const bool exact_only = (flags & NGPD_KNN_EXACT_ONLY) != 0;
     if (k <= 1) launch_knn<1>(G, query, order, m, k, skip, idx_out, d2_out, stream);
     else if (k <= 4) launch_knn<4>(G, query, order, m, k, skip, idx_out, d2_out, stream);
-    else if (k <= 8) launch_knn<8>(G, query, order, m, k, skip, idx_out, d2_out, stream);
-    else if (k <= 16) launch_knn<16>(G, query, order, m, k, skip, idx_out, d2_out, stream);
-    else if (k <= 32) launch_knn<32>(G, query, order, m, k, skip, idx_out, d2_out, stream);
+    else if (k <= 8) { if (exact_only) launch_knn<8>(G, query, order, m, k, skip, idx_out, d2_out, stream); else rc = launch_knn_fast<8>(G, query, order, m, k, skip, idx_out, d2_out, stream); }
+    else if (k <= 16) { if (exact_only) launch_knn<16>(G, query, order, m, k, skip, idx_out, d2_out, stream); else rc = launch_knn_fast<16>(G, query, order, m, k, skip, idx_out, d2_out, stream); }
+    else if (k <= 32) { if (exact_only) launch_knn<32>(G, query, order, m, k, skip, idx_out, d2_out, stream); else rc = launch_knn_fast<32>(G, query, order, m, k, skip, idx_out, d2_out, stream); }
     else launch_knn<64>(G, query, order, m, k, skip, idx_out, d2_out, stream);
+    if (rc) return rc;
     NGPD_CUDA_OK(cudaGetLastError());
     if (order) NGPD_CUDA_OK(cudaFreeAsync(order, stream));
     return 0;

@@ -9,7 +9,8 @@
 // `owned` (optional) marks the rows this rank computes; the remaining rows are halo copies of points owned by
 // another GPU, refreshed between phases by ngpd_session_{export,import}_rows.
 #include <vector>
-#include "knn.cuh"
+#include <algorithm>
+#include "knn_fast.cuh"
 #include "point_math.cuh"
 #include "../../include/ngpd.h"
 
@@ -27,6 +28,8 @@ struct ngpd_session {
     uint8_t* owned = nullptr; // nullable
     int32_t* idx = nullptr;
     int idx_k = 0;
+    int32_t* fix = nullptr;   // n entries + 1 counter: queries the lockstep search hands to the exact search
+    bool exact_only = false;
     double* acc = nullptr;    // 4 doubles
     float* cd = nullptr;      // centre xyz, delta
     int launches = 0;
@@ -66,6 +69,45 @@ __global__ void __launch_bounds__(128) session_knn_kernel(GridView g, const floa
 #pragma unroll
     for (int a = 0; a < K; ++a)
         if (a < k) row[a] = top.id[a] >= 0 ? top.id[a] : (int32_t)s;   // fewer than k tree points: pad with self
+}
+
+template <int K>
+__global__ void __launch_bounds__(KF_THREADS) session_knn_fast_kernel(GridView g, const float4* __restrict__ pos, const uint8_t* __restrict__ owned,
+                                                                      int64_t n, int k, int32_t* __restrict__ idx, int32_t* __restrict__ fix_list,
+                                                                      int32_t* __restrict__ fix_count) {
+    __shared__ KfShared sm;
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool active = s < n && (!owned || owned[s]);
+    float4 q = active ? __ldg(pos + s) : make_float4(0.f, 0.f, 0.f, 0.f);
+    Near<K> top;
+    top.init();
+    bool ok = knn_lockstep<K>(top, sm, g, q.x, q.y, q.z, active, -1);
+    double ex[K];
+    near_finalize<K>(top, g.pts, q.x, q.y, q.z, ex);
+    if (active && ok) {
+        int32_t* row = idx + s * k;
+#pragma unroll
+        for (int a = 0; a < K; ++a)
+            if (a < k) row[a] = top.id[a];
+    }
+    fix_append(active && !ok, (int)s, fix_list, fix_count);
+}
+
+template <int K>
+__global__ void __launch_bounds__(128) session_knn_fix_kernel(GridView g, const float4* __restrict__ pos, int k, int32_t* __restrict__ idx,
+                                                              const int32_t* __restrict__ fix_list, const int32_t* __restrict__ fix_count) {
+    const int cnt = *fix_count;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+        int64_t s = fix_list[i];
+        float4 q = __ldg(pos + s);
+        TopK<K> top;
+        top.init();
+        knn_search<K>(top, g, (double)q.x, (double)q.y, (double)q.z, -1);
+        int32_t* row = idx + s * k;
+#pragma unroll
+        for (int a = 0; a < K; ++a)
+            if (a < k) row[a] = top.id[a] >= 0 ? top.id[a] : (int32_t)s;
+    }
 }
 
 // stage 1: filtered NVT on the current normals, smoothed normal out
@@ -209,11 +251,28 @@ static int ensure_idx(ngpd_session* S, int k) {
     return 0;
 }
 
+template <int K>
+static void run_knn_fast(ngpd_session* S, int k, int32_t* idx, cudaStream_t st) {
+    const GridView& g = S->grid->v;
+    const float4* p = S->pos[S->cur];
+    int32_t* cnt = S->fix + S->n;
+    cudaMemsetAsync(cnt, 0, sizeof(int32_t), st);
+    session_knn_fast_kernel<K><<<(unsigned)cdiv(S->n, KF_THREADS), KF_THREADS, 0, st>>>(g, p, S->owned, S->n, k, idx, S->fix, cnt);
+    int blocks = (int)std::min<int64_t>(cdiv(S->n, 128), (int64_t)num_sms() * 8);
+    session_knn_fix_kernel<K><<<blocks, 128, 0, st>>>(g, p, k, idx, S->fix, cnt);
+}
+
 static int run_knn(ngpd_session* S, int k, int32_t* idx, cudaStream_t st) {
     unsigned b = (unsigned)cdiv(S->n, 128);
     const GridView& g = S->grid->v;
     const float4* p = S->pos[S->cur];
-    if (k <= 4) session_knn_kernel<4><<<b, 128, 0, st>>>(g, p, S->owned, S->n, k, idx);
+    const bool fast = !S->exact_only && k > 4 && k <= 32;
+    if (fast) {
+        if (k <= 8) run_knn_fast<8>(S, k, idx, st);
+        else if (k <= 16) run_knn_fast<16>(S, k, idx, st);
+        else run_knn_fast<32>(S, k, idx, st);
+    }
+    else if (k <= 4) session_knn_kernel<4><<<b, 128, 0, st>>>(g, p, S->owned, S->n, k, idx);
     else if (k <= 8) session_knn_kernel<8><<<b, 128, 0, st>>>(g, p, S->owned, S->n, k, idx);
     else if (k <= 16) session_knn_kernel<16><<<b, 128, 0, st>>>(g, p, S->owned, S->n, k, idx);
     else if (k <= 32) session_knn_kernel<32><<<b, 128, 0, st>>>(g, p, S->owned, S->n, k, idx);
@@ -229,7 +288,7 @@ using namespace ngpd;
 extern "C" __attribute__((visibility("default"))) int ngpd_session_destroy(ngpd_session_t* S) {
     if (!S) return 0;
     if (S->grid) ngpd_grid_destroy(S->grid);
-    void* bufs[] = {S->pos[0], S->pos[1], S->nrm, S->fn, S->edge, S->label, S->owned, S->idx, S->acc, S->cd};
+    void* bufs[] = {S->pos[0], S->pos[1], S->nrm, S->fn, S->edge, S->label, S->owned, S->idx, S->acc, S->cd, S->fix};
     for (void* b : bufs) if (b) cudaFree(b);
     delete S;
     return 0;
@@ -254,6 +313,7 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_create(const 
     if (e == cudaSuccess) e = cudaMalloc(&S->label, (size_t)n);
     if (e == cudaSuccess) e = cudaMalloc(&S->acc, 4 * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&S->cd, 4 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&S->fix, ((size_t)n + 1) * sizeof(int32_t));
     if (e != cudaSuccess) { set_error("ngpd_session_create: %s", cudaGetErrorString(e)); ngpd_session_destroy(S); return -2; }
     NGPD_CUDA_OK(cudaMemsetAsync(S->label, 0, (size_t)n, st));
     NGPD_CUDA_OK(cudaMemsetAsync(S->nrm, 0, b4, st));
@@ -311,7 +371,7 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_phase_feature
         if (rc) return rc;
         { ProfScope ps(S, st, 1);
           session_nvt_smooth_kernel<<<b, 128, 0, st>>>(pos, Quad4{S->nrm}, S->owned, S->idx, S->n, kf, p->x_thresh, p->tau, p->damp, S->fn); }
-        S->launches += 2;
+        S->launches += S->exact_only ? 2 : 3;
     } else {
         { ProfScope ps(S, st, 2);
           session_nvt_classify_kernel<<<b, 128, 0, st>>>(pos, Quad4{S->fn}, S->owned, S->idx, S->n, kf, p->x_thresh, p->scale, S->label, S->edge); }
@@ -336,7 +396,7 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_phase_flat_sc
     } else {
         session_center_kernel<<<1, 1, 0, st>>>(S->acc, S->cd);
         session_class_max_kernel<<<strided(S->n, 256), 256, 0, st>>>(pos, S->owned, S->label, key, S->idx, S->n, S->idx_k, p->k_update, S->cd);
-        S->launches += 2;
+        S->launches += S->exact_only ? 2 : 3;
     }
     NGPD_CUDA_OK(cudaGetLastError());
     return 0;
@@ -398,6 +458,21 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_mean_edge_len
     NGPD_CUDA_OK(cudaFreeAsync(acc, st));
     out_host[0] = h[0]; out_host[1] = h[1];   // {sum of edge lengths, edge count}: callers divide (and all-reduce first on multi-GPU)
     return 0;
+}
+
+// knn_mode 0: lockstep fast path + exact fix-up (default); 1: exact shell search for every query
+extern "C" __attribute__((visibility("default"))) int ngpd_session_set_knn_mode(ngpd_session_t* S, int mode) {
+    NGPD_REQUIRE(S, "ngpd_session_set_knn_mode: NULL session");
+    S->exact_only = mode == 1;
+    return 0;
+}
+// number of queries the last kNN pass handed to the exact search (synchronises the stream)
+extern "C" __attribute__((visibility("default"))) int ngpd_session_last_fixups(ngpd_session_t* S, void* stream_) {
+    if (!S) return -1;
+    int32_t c = 0;
+    if (cudaMemcpyAsync(&c, S->fix + S->n, sizeof(c), cudaMemcpyDeviceToHost, (cudaStream_t)stream_) != cudaSuccess) return -1;
+    cudaStreamSynchronize((cudaStream_t)stream_);
+    return c;
 }
 
 extern "C" __attribute__((visibility("default"))) int ngpd_session_set_profiling(ngpd_session_t* S, int on) {

@@ -230,6 +230,7 @@ class SlabSession:
         import ctypes
         lib, L, p = self._lib.load(), self._lib, self.params
         h, st = self.session._h, L.stream
+        self.launches = 0
         ref = ctypes.byref(p)
         L.check(lib.ngpd_session_phase_features(h, ref, 0, st()), "phase_features 0")
         self._refresh(2)                                        # neighbours' smoothed normals

@@ -108,6 +108,30 @@ def test_knn_random_clouds_bit_exact(ng, kind, k):
     assert np.array_equal(d2.cpu().numpy(), ref_d2)
 
 
+@pytest.mark.parametrize("k", [8, 16, 32])
+def test_knn_fast_path_equals_exact_search(ng, k):
+    """the warp-lockstep fast path (+ fix-up list) returns exactly the rows of the exact shell search"""
+    n = 600_000
+    tree = cu(surface_cloud(n, 31, noise=0.002))
+    query = tree + 0.001 * torch.randn_like(tree)
+    g = ng._lib.Grid(tree, k)
+    fast, d_fast = g.knn(query, k, ng._lib.KNN_QUERY_IS_TREE, with_d2=True)
+    exact, d_exact = g.knn(query, k, ng._lib.KNN_QUERY_IS_TREE | ng._lib.KNN_EXACT_ONLY, with_d2=True)
+    assert torch.equal(fast, exact) and torch.equal(d_fast, d_exact)
+    # random (incoherent) query order and a foreign query set go through the ordering pass
+    other = cu(surface_cloud(50_000, 32, noise=0.01))
+    assert torch.equal(g.knn(other, k), g.knn(other, k, ng._lib.KNN_EXACT_ONLY))
+    sess = ng._lib.Session(tree, k)
+    sess.set_state(query, torch.nn.functional.normalize(torch.randn_like(tree), dim=1))
+    s1, c1 = sess.mean_edge_length_parts(k)
+    fix = sess.last_fixups()
+    sess.set_knn_mode(True)
+    s2, c2 = sess.mean_edge_length_parts(k)
+    print(f"\nk={k}: {fix} of {n} queries ({fix / n:.3%}) went to the exact fix-up pass")
+    assert c1 == c2 and abs(s1 - s2) <= 1e-9 * abs(s2)
+    assert fix < 0.25 * n
+
+
 def test_knn_fewer_points_than_k(ng):
     tree = np.random.default_rng(1).uniform(0, 1, (5, 3)).astype(np.float32)
     got = ng._lib.Grid(cu(tree), 8).knn(cu(tree), 8).cpu().numpy()
@@ -352,7 +376,7 @@ def test_session_labels_vs_reference(ng, fandisk):
     assert (angle_between(fn.cpu().numpy(), fandisk["it0_f_n"]) > 1e-4).mean() < 0.0082
     err = np.abs(pos.cpu().numpy() - fandisk["it0_pos_after_class2"]).max(axis=1) / np.abs(fandisk["pos0"]).max()
     assert (err > 1e-5).mean() < 0.01
-    assert 8 <= sess.launch_count() <= 12
+    assert 8 <= sess.launch_count() <= 13
 
 
 def test_until_minimum_error_loop(ng, until_min):
