@@ -41,7 +41,8 @@ __global__ void __launch_bounds__(KF_THREADS) knn_fast_kernel(GridView g, const 
     if (active) { qx = __ldg(query + 3 * qi); qy = __ldg(query + 3 * qi + 1); qz = __ldg(query + 3 * qi + 2); }
     Near<K> top;
     top.init();
-    bool ok = knn_lockstep<K>(top, sm, g, qx, qy, qz, active, skip_self ? (int)qi : -1);
+    bool ok = skip_self ? knn_lockstep<K, true>(top, sm, g, qx, qy, qz, active, (int)qi)
+                        : knn_lockstep<K, false>(top, sm, g, qx, qy, qz, active, -1);
     double ex[K];
     near_finalize<K>(top, g.pts, qx, qy, qz, ex);
     if (active && ok) {

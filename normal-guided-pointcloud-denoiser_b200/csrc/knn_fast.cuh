@@ -28,9 +28,10 @@ template <int K>
 struct Near {
     float d[K];
     int id[K];
-    __device__ __forceinline__ void init() {
+    // `bound`: no neighbour of the final answer is farther than this (INFINITY when nothing is known)
+    __device__ __forceinline__ void init(float bound = INFINITY) {
 #pragma unroll
-        for (int a = 0; a < K; ++a) { d[a] = INFINITY; id[a] = -1; }
+        for (int a = 0; a < K; ++a) { d[a] = bound; id[a] = -1; }
     }
 };
 
@@ -70,31 +71,45 @@ __device__ __forceinline__ void near_flush(Near<K>& t, KfShared& sm, int& cnt, f
     cnt = 0;
 }
 
-template <int K>
+template <int K, bool SELF, bool TAIL>
+__device__ __forceinline__ void near_group(Near<K>& t, KfShared& sm, int& cnt, float& rej, const float4* __restrict__ pts,
+                                           int j0, int e, float qx, float qy, float qz, bool active, int self_orig) {
+    const int tid = threadIdx.x;
+    float4 p[KF_GROUP];
+#pragma unroll
+    for (int u = 0; u < KF_GROUP; ++u) p[u] = __ldg(pts + (TAIL ? min(j0 + u, e - 1) : j0 + u));
+    const float worst = t.d[K - 1];
+#pragma unroll
+    for (int u = 0; u < KF_GROUP; ++u) {
+        float dx = p[u].x - qx, dy = p[u].y - qy, dz = p[u].z - qz;
+        float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        bool valid = active;
+        if (TAIL) valid = valid && (j0 + u < e);
+        if (SELF) valid = valid && (__float_as_int(p[u].w) != self_orig);
+        bool take = valid && d2 < worst;
+        if (take) { sm.d[cnt][tid] = d2; sm.j[cnt][tid] = j0 + u; ++cnt; }
+        if (valid && !take) rej = fminf(rej, d2);
+    }
+}
+
+template <int K, bool SELF>
 __device__ __forceinline__ void near_stream(Near<K>& t, KfShared& sm, int& cnt, float& rej, const float4* __restrict__ pts,
                                             int s, int e, float qx, float qy, float qz, bool active, int self_orig) {
-    const int tid = threadIdx.x;
-    for (int j0 = s; j0 < e; j0 += KF_GROUP) {
+    int j0 = s;
+    for (; j0 + KF_GROUP <= e; j0 += KF_GROUP) {
         if (__any_sync(FULL, cnt > KF_BUF - KF_GROUP)) near_flush<K>(t, sm, cnt, rej);
-        float4 p[KF_GROUP];
-#pragma unroll
-        for (int u = 0; u < KF_GROUP; ++u) p[u] = __ldg(pts + min(j0 + u, e - 1));
-        const float worst = t.d[K - 1];
-#pragma unroll
-        for (int u = 0; u < KF_GROUP; ++u) {
-            float dx = p[u].x - qx, dy = p[u].y - qy, dz = p[u].z - qz;
-            float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-            bool valid = active && (j0 + u < e) && (__float_as_int(p[u].w) != self_orig);
-            if (valid) {
-                if (d2 < worst) { sm.d[cnt][tid] = d2; sm.j[cnt][tid] = j0 + u; ++cnt; }
-                else rej = fminf(rej, d2);
-            }
-        }
+        near_group<K, SELF, false>(t, sm, cnt, rej, pts, j0, e, qx, qy, qz, active, self_orig);
+    }
+    if (j0 < e) {
+        if (__any_sync(FULL, cnt > KF_BUF - KF_GROUP)) near_flush<K>(t, sm, cnt, rej);
+        near_group<K, SELF, true>(t, sm, cnt, rej, pts, j0, e, qx, qy, qz, active, self_orig);
     }
 }
 
 // Lockstep search of the lanes' 3x3x3 blocks.  Returns true when this lane's list is final up to the exact re-sort.
-template <int K>
+// Rows are visited in two passes: first the rows that hold the lanes' own cells (their candidates are the nearest, so
+// the lists fill with good values and the accept threshold is tight before the surrounding shell streams by).
+template <int K, bool SELF>
 __device__ __forceinline__ bool knn_lockstep(Near<K>& t, KfShared& sm, const GridView& g, float qx, float qy, float qz,
                                              bool active, int self_orig) {
     const double rx = (double)qx - g.ox, ry = (double)qy - g.oy, rz = (double)qz - g.oz;
@@ -102,37 +117,45 @@ __device__ __forceinline__ bool knn_lockstep(Near<K>& t, KfShared& sm, const Gri
     const int cy = min(max((int)floor(ry * g.inv_h), 0), g.ny - 1);
     const int cz = min(max((int)floor(rz * g.inv_h), 0), g.nz - 1);
     const int BIG = 1 << 29;
-    int lx = max(__reduce_min_sync(FULL, active ? cx - 1 : BIG), 0), hx = min(__reduce_max_sync(FULL, active ? cx + 1 : -BIG), g.nx - 1);
-    int ly = max(__reduce_min_sync(FULL, active ? cy - 1 : BIG), 0), hy = min(__reduce_max_sync(FULL, active ? cy + 1 : -BIG), g.ny - 1);
-    int lz = max(__reduce_min_sync(FULL, active ? cz - 1 : BIG), 0), hz = min(__reduce_max_sync(FULL, active ? cz + 1 : -BIG), g.nz - 1);
-    if (hx < lx) return false;                                        // no active lane in this warp
-    if ((hy - ly + 1) * (hz - lz + 1) > 576 || (hx - lx + 1) > 48) return false;   // lanes far apart (curve jump): exact path
+    const int my0 = __reduce_min_sync(FULL, active ? cy : BIG), my1 = __reduce_max_sync(FULL, active ? cy : -BIG);
+    const int mz0 = __reduce_min_sync(FULL, active ? cz : BIG), mz1 = __reduce_max_sync(FULL, active ? cz : -BIG);
+    if (my1 < my0) return false;                                      // no active lane in this warp
+    const int ly = max(my0 - 1, 0), hy = min(my1 + 1, g.ny - 1), lz = max(mz0 - 1, 0), hz = min(mz1 + 1, g.nz - 1);
+    {
+        int mx0 = __reduce_min_sync(FULL, active ? cx : BIG), mx1 = __reduce_max_sync(FULL, active ? cx : -BIG);
+        if ((hy - ly + 1) * (hz - lz + 1) > 576 || (mx1 - mx0 + 3) > 48) return false;   // lanes far apart (curve jump): exact path
+    }
     int cnt = 0;
     float rej = INFINITY;
-    for (int z = lz; z <= hz; ++z) {
-        for (int y = ly; y <= hy; ++y) {
-            bool rel = active && abs(z - cz) <= 1 && abs(y - cy) <= 1;
-            if (!__any_sync(FULL, rel)) continue;
-            int x0 = max(__reduce_min_sync(FULL, rel ? cx - 1 : BIG), 0);
-            int x1 = min(__reduce_max_sync(FULL, rel ? cx + 1 : -BIG), g.nx - 1);
-            const int64_t trow = ((int64_t)(z >> 3) * g.tby + (y >> 3)) * g.tbx;
-            const int lrow = ((z & 7) << 6) | ((y & 7) << 3);
-            while (x0 <= x1) {
-                int xe = min(x1, (x0 | 7));
-                int b = __ldg(g.top + trow + (x0 >> 3));
-                if (b >= 0) {
-                    const int* f = g.fine + (int64_t)b * 513 + lrow;
-                    int s = __ldg(f + (x0 & 7)), e = __ldg(f + (xe & 7) + 1);
-                    if (e > s) near_stream<K>(t, sm, cnt, rej, g.pts, s, e, qx, qy, qz, active, self_orig);
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int z = lz; z <= hz; ++z) {
+            for (int y = ly; y <= hy; ++y) {
+                const bool core = (y >= my0 && y <= my1 && z >= mz0 && z <= mz1);
+                if (core != (pass == 0)) continue;
+                bool rel = active && abs(z - cz) <= 1 && abs(y - cy) <= 1;
+                if (!__any_sync(FULL, rel)) continue;
+                int x0 = max(__reduce_min_sync(FULL, rel ? cx - 1 : BIG), 0);
+                int x1 = min(__reduce_max_sync(FULL, rel ? cx + 1 : -BIG), g.nx - 1);
+                const int64_t trow = ((int64_t)(z >> 3) * g.tby + (y >> 3)) * g.tbx;
+                const int lrow = ((z & 7) << 6) | ((y & 7) << 3);
+                while (x0 <= x1) {
+                    int xe = min(x1, (x0 | 7));
+                    int b = __ldg(g.top + trow + (x0 >> 3));
+                    if (b >= 0) {
+                        const int* f = g.fine + (int64_t)b * 513 + lrow;
+                        int s = __ldg(f + (x0 & 7)), e = __ldg(f + (xe & 7) + 1);
+                        if (e > s) near_stream<K, SELF>(t, sm, cnt, rej, g.pts, s, e, qx, qy, qz, active, self_orig);
+                    }
+                    x0 = xe + 1;
                 }
-                x0 = xe + 1;
             }
         }
     }
     near_flush<K>(t, sm, cnt, rej);
     if (!active) return false;
-    // the lane saw (at least) every point of its own 3x3x3 block: final iff the k-th distance lies inside that block
-    // and no rejected candidate is within the fp32 evaluation error of it
+    // the lane saw (at least) every point of its own 3x3x3 block: final iff the list is full, its k-th distance lies
+    // inside that block, and no rejected candidate is within the fp32 evaluation error of it
     const float worst = t.d[K - 1];
     double reach = DBL_MAX;
     if (cx - 1 > 0) reach = fmin(reach, rx - (double)(cx - 1) * g.h);
@@ -142,9 +165,10 @@ __device__ __forceinline__ bool knn_lockstep(Near<K>& t, KfShared& sm, const Gri
     if (cz - 1 > 0) reach = fmin(reach, rz - (double)(cz - 1) * g.h);
     if (cz + 1 < g.nz - 1) reach = fmin(reach, (double)(cz + 2) * g.h - rz);
     const double wmax = (double)worst * (1.0 + 2e-6);
-    bool inside = (reach == DBL_MAX) ? (worst < INFINITY) : (reach > 0.0 && wmax < (reach - g.h * 1e-9) * (reach - g.h * 1e-9));
+    const double rr = reach - g.h * 1e-9;
+    bool inside = (reach == DBL_MAX) ? true : (rr > 0.0 && wmax < rr * rr);
     bool clear = (double)rej > wmax;
-    return inside && clear;
+    return t.id[K - 1] >= 0 && inside && clear;
 }
 
 // exact re-evaluation and ordering of the k kept candidates: (fp64 distance, original index)

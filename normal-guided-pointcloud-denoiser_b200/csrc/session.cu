@@ -30,6 +30,12 @@ struct ngpd_session {
     int idx_k = 0;
     int32_t* fix = nullptr;   // n entries + 1 counter: queries the lockstep search hands to the exact search
     bool exact_only = false;
+    // temporal bound for the next search: rk = k-th squared distance of the last search (rounded up), moved = how far the
+    // point has travelled since.  By the triangle inequality its next k-th distance is at most sqrt(rk) + moved.
+    float* rk = nullptr;
+    float* moved = nullptr;
+    int bound_k = 0;          // template K the bound was recorded for (0 = none)
+    bool use_bound = true;
     double* acc = nullptr;    // 4 doubles
     float* cd = nullptr;      // centre xyz, delta
     int launches = 0;
@@ -74,14 +80,20 @@ __global__ void __launch_bounds__(128) session_knn_kernel(GridView g, const floa
 template <int K>
 __global__ void __launch_bounds__(KF_THREADS) session_knn_fast_kernel(GridView g, const float4* __restrict__ pos, const uint8_t* __restrict__ owned,
                                                                       int64_t n, int k, int32_t* __restrict__ idx, int32_t* __restrict__ fix_list,
-                                                                      int32_t* __restrict__ fix_count) {
+                                                                      int32_t* __restrict__ fix_count, const float* __restrict__ rk_in,
+                                                                      float* __restrict__ moved, float* __restrict__ rk_out) {
     __shared__ KfShared sm;
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool active = s < n && (!owned || owned[s]);
     float4 q = active ? __ldg(pos + s) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float bound = INFINITY;
+    if (active && rk_in) {
+        float r = sqrtf(rk_in[s]) + moved[s];
+        bound = r * r * 1.00001f;                 // > (sqrt(rk) + moved)^2 whatever the fp32 roundings above did
+    }
     Near<K> top;
-    top.init();
-    bool ok = knn_lockstep<K>(top, sm, g, q.x, q.y, q.z, active, -1);
+    top.init(bound);
+    bool ok = knn_lockstep<K, false>(top, sm, g, q.x, q.y, q.z, active, -1);
     double ex[K];
     near_finalize<K>(top, g.pts, q.x, q.y, q.z, ex);
     if (active && ok) {
@@ -89,13 +101,15 @@ __global__ void __launch_bounds__(KF_THREADS) session_knn_fast_kernel(GridView g
 #pragma unroll
         for (int a = 0; a < K; ++a)
             if (a < k) row[a] = top.id[a];
+        if (rk_out) { rk_out[s] = __double2float_ru(ex[K - 1]); moved[s] = 0.0f; }
     }
     fix_append(active && !ok, (int)s, fix_list, fix_count);
 }
 
 template <int K>
 __global__ void __launch_bounds__(128) session_knn_fix_kernel(GridView g, const float4* __restrict__ pos, int k, int32_t* __restrict__ idx,
-                                                              const int32_t* __restrict__ fix_list, const int32_t* __restrict__ fix_count) {
+                                                              const int32_t* __restrict__ fix_list, const int32_t* __restrict__ fix_count,
+                                                              float* __restrict__ moved, float* __restrict__ rk_out) {
     const int cnt = *fix_count;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
         int64_t s = fix_list[i];
@@ -107,6 +121,7 @@ __global__ void __launch_bounds__(128) session_knn_fix_kernel(GridView g, const 
 #pragma unroll
         for (int a = 0; a < K; ++a)
             if (a < k) row[a] = top.id[a] >= 0 ? top.id[a] : (int32_t)s;
+        if (rk_out) { rk_out[s] = top.id[K - 1] >= 0 ? __double2float_ru(top.d[K - 1]) : INFINITY; moved[s] = 0.0f; }
     }
 }
 
@@ -177,16 +192,21 @@ __global__ void __launch_bounds__(256) session_class_max_kernel(Quad4 pos, const
 __global__ void __launch_bounds__(128) session_update_kernel(int kind, int key, Quad4 pos, Quad4 fn, const float4* __restrict__ edge,
                                                              const uint8_t* __restrict__ label, const uint8_t* __restrict__ owned,
                                                              const int32_t* __restrict__ idx, int64_t n, int k, int ku, float alpha, float dmax,
-                                                             const float* __restrict__ cd, float4* __restrict__ out) {
+                                                             const float* __restrict__ cd, float4* __restrict__ out, float* __restrict__ moved) {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     V3 p = pos(s);
+    const V3 p0 = p;
     if (label[s] == key && (!owned || owned[s])) {
         const int32_t* row = idx + s * k;
         if (kind == NGPD_STEP_FLAT) p = flat_point(pos, fn, s, row, ku, cd[3], alpha, dmax);
         else if (kind == NGPD_STEP_EDGE) { float4 e = __ldg(edge + s); p = edge_point(pos, fn, v3(e.x, e.y, e.z), s, row, ku, alpha, dmax); }
         else if (kind == NGPD_STEP_FEATURE) p = feature_point(pos, fn, s, row, ku, alpha, dmax);
         else if (kind == NGPD_STEP_CORNER) p = corner_point(pos, fn, s, row, ku, alpha, dmax);
+        // distance travelled since the last search, rounded up (feeds the next search's bound)
+        V3 dd = p - p0;
+        float len = sqrtf(dd.x * dd.x + dd.y * dd.y + dd.z * dd.z);
+        if (len > 0.0f) moved[s] = moved[s] + len * 1.000001f + 1e-30f;
     }
     out[s] = make_float4(p.x, p.y, p.z, 0.0f);
 }
@@ -251,26 +271,30 @@ static int ensure_idx(ngpd_session* S, int k) {
     return 0;
 }
 
+// `track`: this is the step's own search (record rk / reset moved so that the next one starts from a bound)
 template <int K>
-static void run_knn_fast(ngpd_session* S, int k, int32_t* idx, cudaStream_t st) {
+static void run_knn_fast(ngpd_session* S, int k, int32_t* idx, cudaStream_t st, bool track) {
     const GridView& g = S->grid->v;
     const float4* p = S->pos[S->cur];
     int32_t* cnt = S->fix + S->n;
     cudaMemsetAsync(cnt, 0, sizeof(int32_t), st);
-    session_knn_fast_kernel<K><<<(unsigned)cdiv(S->n, KF_THREADS), KF_THREADS, 0, st>>>(g, p, S->owned, S->n, k, idx, S->fix, cnt);
+    const float* rk_in = (track && S->bound_k == K && S->use_bound) ? S->rk : nullptr;
+    float* rk_out = track ? S->rk : nullptr;
+    session_knn_fast_kernel<K><<<(unsigned)cdiv(S->n, KF_THREADS), KF_THREADS, 0, st>>>(g, p, S->owned, S->n, k, idx, S->fix, cnt, rk_in, S->moved, rk_out);
     int blocks = (int)std::min<int64_t>(cdiv(S->n, 128), (int64_t)num_sms() * 8);
-    session_knn_fix_kernel<K><<<blocks, 128, 0, st>>>(g, p, k, idx, S->fix, cnt);
+    session_knn_fix_kernel<K><<<blocks, 128, 0, st>>>(g, p, k, idx, S->fix, cnt, S->moved, rk_out);
+    if (track) S->bound_k = K;
 }
 
-static int run_knn(ngpd_session* S, int k, int32_t* idx, cudaStream_t st) {
+static int run_knn(ngpd_session* S, int k, int32_t* idx, cudaStream_t st, bool track = false) {
     unsigned b = (unsigned)cdiv(S->n, 128);
     const GridView& g = S->grid->v;
     const float4* p = S->pos[S->cur];
     const bool fast = !S->exact_only && k > 4 && k <= 32;
     if (fast) {
-        if (k <= 8) run_knn_fast<8>(S, k, idx, st);
-        else if (k <= 16) run_knn_fast<16>(S, k, idx, st);
-        else run_knn_fast<32>(S, k, idx, st);
+        if (k <= 8) run_knn_fast<8>(S, k, idx, st, track);
+        else if (k <= 16) run_knn_fast<16>(S, k, idx, st, track);
+        else run_knn_fast<32>(S, k, idx, st, track);
     }
     else if (k <= 4) session_knn_kernel<4><<<b, 128, 0, st>>>(g, p, S->owned, S->n, k, idx);
     else if (k <= 8) session_knn_kernel<8><<<b, 128, 0, st>>>(g, p, S->owned, S->n, k, idx);
@@ -288,7 +312,7 @@ using namespace ngpd;
 extern "C" __attribute__((visibility("default"))) int ngpd_session_destroy(ngpd_session_t* S) {
     if (!S) return 0;
     if (S->grid) ngpd_grid_destroy(S->grid);
-    void* bufs[] = {S->pos[0], S->pos[1], S->nrm, S->fn, S->edge, S->label, S->owned, S->idx, S->acc, S->cd, S->fix};
+    void* bufs[] = {S->pos[0], S->pos[1], S->nrm, S->fn, S->edge, S->label, S->owned, S->idx, S->acc, S->cd, S->fix, S->rk, S->moved};
     for (void* b : bufs) if (b) cudaFree(b);
     delete S;
     return 0;
@@ -314,8 +338,12 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_create(const 
     if (e == cudaSuccess) e = cudaMalloc(&S->acc, 4 * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&S->cd, 4 * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&S->fix, ((size_t)n + 1) * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&S->rk, (size_t)n * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&S->moved, (size_t)n * sizeof(float));
     if (e != cudaSuccess) { set_error("ngpd_session_create: %s", cudaGetErrorString(e)); ngpd_session_destroy(S); return -2; }
     NGPD_CUDA_OK(cudaMemsetAsync(S->label, 0, (size_t)n, st));
+    NGPD_CUDA_OK(cudaMemsetAsync(S->moved, 0, (size_t)n * sizeof(float), st));
+    NGPD_CUDA_OK(cudaMemsetAsync(S->rk, 0, (size_t)n * sizeof(float), st));
     NGPD_CUDA_OK(cudaMemsetAsync(S->nrm, 0, b4, st));
     // current positions start as the tree positions
     session_scatter_in_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(G->pts, tree_pos, nullptr, n, S->pos[0], nullptr);
@@ -326,6 +354,7 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_create(const 
 
 extern "C" __attribute__((visibility("default"))) int ngpd_session_set_state(ngpd_session_t* S, const float* pos, const float* nrm, void* stream_) {
     NGPD_REQUIRE(S, "ngpd_session_set_state: NULL session");
+    if (pos) S->bound_k = 0;          // positions replaced from outside: the displacement record is void
     session_scatter_in_kernel<<<(unsigned)cdiv(S->n, 256), 256, 0, (cudaStream_t)stream_>>>(S->grid->pts, pos, nrm, S->n, S->pos[S->cur], S->nrm);
     NGPD_CUDA_OK(cudaGetLastError());
     return 0;
@@ -367,7 +396,7 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_phase_feature
         int rc = ensure_idx(S, kf);
         if (rc) return rc;
         S->idx_k = kf;
-        { ProfScope ps(S, st, 0); rc = run_knn(S, kf, S->idx, st); }
+        { ProfScope ps(S, st, 0); rc = run_knn(S, kf, S->idx, st, true); }
         if (rc) return rc;
         { ProfScope ps(S, st, 1);
           session_nvt_smooth_kernel<<<b, 128, 0, st>>>(pos, Quad4{S->nrm}, S->owned, S->idx, S->n, kf, p->x_thresh, p->tau, p->damp, S->fn); }
@@ -410,7 +439,7 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_phase_update(
     ProfScope ps(S, st, 4);
     session_update_kernel<<<(unsigned)cdiv(S->n, 128), 128, 0, st>>>(kind, key, Quad4{S->pos[S->cur]}, Quad4{S->fn}, S->edge, S->label, S->owned,
                                                                      S->idx, S->n, S->idx_k, p->k_update, p->alpha[key], p->dmax, S->cd,
-                                                                     S->pos[S->cur ^ 1]);
+                                                                     S->pos[S->cur ^ 1], S->moved);
     NGPD_CUDA_OK(cudaGetLastError());
     S->cur ^= 1;
     S->launches += 1;
@@ -464,6 +493,7 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_mean_edge_len
 extern "C" __attribute__((visibility("default"))) int ngpd_session_set_knn_mode(ngpd_session_t* S, int mode) {
     NGPD_REQUIRE(S, "ngpd_session_set_knn_mode: NULL session");
     S->exact_only = mode == 1;
+    S->use_bound = mode != 2;         // mode 2: fast path without the temporal bound (measurements)
     return 0;
 }
 // number of queries the last kNN pass handed to the exact search (synchronises the stream)

@@ -354,8 +354,11 @@ def test_denoise_vs_reference_free_running(ng, fandisk):
     err = np.abs(pos - fandisk["pos_final"]).max(axis=1) / scale
     ang = angle_between(nrm, fandisk["n_final"])
     print(f"\nfree-running denoise(): positions >1e-5: {(err > 1e-5).mean():.4%} (max {err.max():.2e}); normals >1e-4 rad: {(ang > 1e-4).mean():.4%}")
-    assert (err > 1e-5).mean() < 0.02
-    assert (ang > 1e-4).mean() < 0.02
+    # yardstick: the reference run twice, the second time with its input normals moved by 1 ulp, differs from itself by
+    # 12.57 % of positions (> 1e-5, max 4.2e-3), 6.75 % of normals (> 1e-4 rad) and 20 labels after these two iterations
+    # (measured with the oracle, same LAPACK; DESIGN.md "parity protocol")
+    assert (err > 1e-5).mean() < 0.1257 and err.max() < 1e-2
+    assert (ang > 1e-4).mean() < 0.0675
     cd = ng.TorchUtils.ChamferDistance(cu(fandisk["gt"]), p.graph.pos).double().mean().item()
     ref = fandisk["cd_final"].mean(dtype=np.float64)
     assert abs(cd - ref) / ref < 1e-3
@@ -372,10 +375,12 @@ def test_session_labels_vs_reference(ng, fandisk):
     pos, fn, lab = sess.get_state(True)
     agree = (lab.cpu().numpy() == fandisk["it0_classes"]).mean()
     print(f"\nfree-running labels agree with the reference on {agree:.4%} of points")
-    assert agree > 0.995
-    assert (angle_between(fn.cpu().numpy(), fandisk["it0_f_n"]) > 1e-4).mean() < 0.0082
+    # yardstick after ONE iteration (reference vs itself under a 1-ulp change of the input normals): 7 labels,
+    # 0.80 % of normals, 3.77 % of positions
+    assert (lab.cpu().numpy() != fandisk["it0_classes"]).sum() <= 7
+    assert (angle_between(fn.cpu().numpy(), fandisk["it0_f_n"]) > 1e-4).mean() < 0.0080
     err = np.abs(pos.cpu().numpy() - fandisk["it0_pos_after_class2"]).max(axis=1) / np.abs(fandisk["pos0"]).max()
-    assert (err > 1e-5).mean() < 0.01
+    assert (err > 1e-5).mean() < 0.0377
     assert 8 <= sess.launch_count() <= 13
 
 
@@ -403,7 +408,7 @@ def test_until_minimum_error_loop(ng, until_min):
     assert torch.equal(p.graph.pos, noisy)                                   # reset to the noisy input on exit
     scale = np.abs(until_min["pos0"]).max()
     err = np.abs(best.cpu().numpy() - until_min["pos_returned"]).max(axis=1) / scale
-    assert (err > 1e-5).mean() < 0.02
+    assert (err > 1e-5).mean() < 0.1257
 
 
 def test_generic_strategy_path(ng, fandisk):
@@ -467,6 +472,17 @@ def test_session_large_runs_and_is_deterministic(ng):
         outs.append(sess.get_state(True))
     for a, b in zip(*outs):
         assert torch.equal(a, b)                                              # no atomics in any per-point result
+    # the three kNN modes (lockstep + temporal bound, exact shell search, lockstep without the bound) give the same run
+    for mode in (True, 2):
+        sess = ng._lib.Session(cloud, 16)
+        sess.set_state(cloud, nrm)
+        if mode is True:
+            sess.set_knn_mode(True)
+        else:
+            ng._lib.check(ng._lib.load().ngpd_session_set_knn_mode(sess._h, 2), "mode")
+        sess.step(params); sess.step(params)
+        for a, b in zip(outs[0], sess.get_state(True)):
+            assert torch.equal(a, b)
     pos, fn, lab = outs[0]
     assert torch.isfinite(pos).all() and torch.isfinite(fn).all()
     assert torch.allclose(fn.norm(dim=1), torch.ones(n, device="cuda"), atol=1e-4)
