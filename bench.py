@@ -96,7 +96,7 @@ def make_input(n, device, seed=1234):
     grid = _lib.Grid(noisy, 12)
     table = grid.knn(noisy, 12, _lib.KNN_SKIP_SELF | _lib.KNN_QUERY_IS_TREE)
     nrm = torch.empty_like(noisy)
-    _lib.check(_lib.load().ngpd_pca_normals(noisy.data_ptr(), table.data_ptr(), None, n, 12, nrm.data_ptr(), None, _lib.stream()), "pca")
+    _lib.check(_lib.load().ngpd_pca_normals(noisy.data_ptr(), table.data_ptr(), None, n, 12, nrm.data_ptr(), None, None, _lib.stream()), "pca")
     flip = (nrm * normal).sum(1) < 0
     nrm[flip] *= -1
     del grid, table, clean, normal

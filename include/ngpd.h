@@ -70,9 +70,12 @@ int ngpd_nn_sqdist(const ngpd_grid_t* grid, const float* query, int64_t m, int f
  * idx[offsets ? offsets[r] .. offsets[r+1] : r*k .. r*k+k) (CSR when offsets != NULL). -------------------- */
 
 /* GraphBuilder.getPVTDecompositionWithKNN, GraphBuilder.py:99-111: covariance of the neighbours about their
- * mean, LAPACK-order eigen-decomposition; normals_out = eigenvector of the smallest eigenvalue. */
+ * mean, LAPACK-order eigen-decomposition; normals_out [m,3] = eigenvector of the smallest eigenvalue;
+ * eigval_out [m,3] ascending and eigvec_out [m,3,3] (columns) are optional (at least one of normals_out /
+ * eigvec_out must be given). */
 int ngpd_pca_normals(const float* pos, const int32_t* idx, const int32_t* offsets, int64_t m, int k,
-                     float* normals_out, float* eigval_out /*nullable [m,3]*/, void* stream);
+                     float* normals_out /*nullable*/, float* eigval_out /*nullable*/, float* eigvec_out /*nullable*/,
+                     void* stream);
 
 /* Decompositionor.getBetterFilteredNVT, Decompositionor.py:278-300.  x_thresh = largest fp32 x with
  * acos(x) > rho.  Outputs: eigval [m,3] ascending, eigvec [m,3,3] (columns), optional tensor [m,3,3]

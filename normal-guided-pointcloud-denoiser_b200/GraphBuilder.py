@@ -64,18 +64,10 @@ class GraphBuilder:
         pos = _lib.dev(g.pos, torch.float32, "graph.pos")
         n = pos.size(0)
         table = edge_index[1].view(-1, k).to(torch.int32).contiguous()
-        # full decomposition through the voting-tensor entry point is not needed: the normal kernel returns the
-        # smallest eigenvector; for the (rarely used) full basis run the generic eigen kernel on the covariances
-        normals = torch.empty((n, 3), dtype=torch.float32, device=pos.device)
         eigval = torch.empty((n, 3), dtype=torch.float32, device=pos.device)
-        _lib.check(_lib.load().ngpd_pca_normals(_lib.ptr(pos), _lib.ptr(table), None, n, k, _lib.ptr(normals), _lib.ptr(eigval),
-                                                _lib.stream()), "ngpd_pca_normals")
-        self._last_normals = normals
-        vj = pos[table.long()]
-        d = vj - vj.mean(dim=1, keepdim=True)
-        cov = torch.einsum("nki,nkj->nij", d, d).contiguous()
         vec = torch.empty((n, 3, 3), dtype=torch.float32, device=pos.device)
-        _lib.check(_lib.load().ngpd_eigh3(_lib.ptr(cov), n, _lib.ptr(eigval), _lib.ptr(vec), _lib.stream()), "ngpd_eigh3")
+        _lib.check(_lib.load().ngpd_pca_normals(_lib.ptr(pos), _lib.ptr(table), None, n, k, None, _lib.ptr(eigval), _lib.ptr(vec),
+                                                _lib.stream()), "ngpd_pca_normals")
         return eigval, vec
 
     def setPVTNormals(self, edge_index: torch.Tensor) -> None:
@@ -85,7 +77,7 @@ class GraphBuilder:
         n = pos.size(0)
         table = edge_index[1].view(-1, k).to(torch.int32).contiguous()
         normals = torch.empty((n, 3), dtype=torch.float32, device=pos.device)
-        _lib.check(_lib.load().ngpd_pca_normals(_lib.ptr(pos), _lib.ptr(table), None, n, k, _lib.ptr(normals), None, _lib.stream()),
+        _lib.check(_lib.load().ngpd_pca_normals(_lib.ptr(pos), _lib.ptr(table), None, n, k, _lib.ptr(normals), None, None, _lib.stream()),
                    "ngpd_pca_normals")
         g.n = normals
 

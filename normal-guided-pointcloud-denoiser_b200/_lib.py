@@ -37,7 +37,7 @@ SIGNATURES = {
     "ngpd_grid_order": (ctypes.c_int, [c_vp, c_vp, c_vp]),
     "ngpd_knn": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.c_int, ctypes.c_int, c_vp, c_vp, c_vp]),
     "ngpd_nn_sqdist": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.c_int, c_vp, c_vp, c_vp]),
-    "ngpd_pca_normals": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, ctypes.c_int, c_vp, c_vp, c_vp]),
+    "ngpd_pca_normals": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, ctypes.c_int, c_vp, c_vp, c_vp, c_vp]),
     "ngpd_nvt": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.c_int, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ngpd_eigh3": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
     "ngpd_smooth_normals": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_vp, c_vp]),

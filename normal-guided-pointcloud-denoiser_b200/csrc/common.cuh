@@ -7,8 +7,10 @@
 #if defined(__CUDACC__)
 #include <cuda_runtime.h>
 #define NGPD_HD __host__ __device__ __forceinline__
+#define NGPD_HD_COLD static __host__ __device__ __noinline__     // rare paths: kept out of line so the hot code stays small
 #else
 #define NGPD_HD inline
+#define NGPD_HD_COLD static inline
 #endif
 
 namespace ngpd {

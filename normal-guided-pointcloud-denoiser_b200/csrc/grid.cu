@@ -359,7 +359,9 @@ static int build_once(ngpd_grid* G, const float* pos, int64_t n, double h, cudaS
     int64_t ntop = (int64_t)v.tbx * v.tby * v.tbz;
     NGPD_CUDA_OK(cudaMalloc(&G->top, ntop * sizeof(int)));
     NGPD_CUDA_OK(cudaMemsetAsync(G->top, 0xff, ntop * sizeof(int), stream));
-    NGPD_CUDA_OK(cudaMalloc(&G->pts, (size_t)n * sizeof(float4)));
+    // 4 padding entries: the streaming k-NN kernel loads candidates four at a time and masks the overrun
+    NGPD_CUDA_OK(cudaMalloc(&G->pts, ((size_t)n + 4) * sizeof(float4)));
+    NGPD_CUDA_OK(cudaMemsetAsync(G->pts + n, 0, 4 * sizeof(float4), stream));
     uint64_t *keys = nullptr, *keys2 = nullptr;
     uint32_t *vals = nullptr, *vals2 = nullptr;
     int *flag = nullptr, *brick_start = nullptr;

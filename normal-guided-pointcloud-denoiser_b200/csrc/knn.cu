@@ -1,5 +1,5 @@
 #include <algorithm>
-#include "knn_fast.cuh"
+#include "knn_stream.cuh"
 #include "../../include/ngpd.h"
 
 namespace ngpd {
@@ -27,34 +27,55 @@ __global__ void __launch_bounds__(128) knn_kernel(GridView g, const float* __res
     }
 }
 
-// fast path: warp-lockstep search (knn_fast.cuh); queries it cannot settle go to `fix_list`
-template <int K>
-__global__ void __launch_bounds__(KF_THREADS) knn_fast_kernel(GridView g, const float* __restrict__ query, const int32_t* __restrict__ qorder,
-                                                              int64_t m, int k, int skip_self, int32_t* __restrict__ idx_out,
-                                                              float* __restrict__ d2_out, int32_t* __restrict__ fix_list,
-                                                              int32_t* __restrict__ fix_count) {
-    __shared__ KfShared sm;
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool active = t < m;
+// fast path, tier 1: per-lane candidate streams over the 3x3x3 block + network selection (knn_stream.cuh); queries it
+// cannot settle go to `fix_list`
+template <int K, int R>
+__device__ __forceinline__ void knn_fast_body(KsShared<R>& sm, const GridView& g, const float* __restrict__ query, const int32_t* __restrict__ qorder,
+                                              int64_t t, bool active, int k, int skip_self, int32_t* __restrict__ idx_out,
+                                              float* __restrict__ d2_out, int32_t* __restrict__ fail_list, int32_t* __restrict__ fail_count) {
     int64_t qi = active ? (qorder ? (int64_t)qorder[t] : t) : 0;
     float qx = 0.f, qy = 0.f, qz = 0.f;
     if (active) { qx = __ldg(query + 3 * qi); qy = __ldg(query + 3 * qi + 1); qz = __ldg(query + 3 * qi + 2); }
-    Near<K> top;
-    top.init();
-    bool ok = skip_self ? knn_lockstep<K, true>(top, sm, g, qx, qy, qz, active, (int)qi)
-                        : knn_lockstep<K, false>(top, sm, g, qx, qy, qz, active, -1);
+    KsTop<K> top;
+    bool ok = skip_self ? knn_stream<K, R, true>(top, sm, g, qx, qy, qz, active, (int)qi, INFINITY)
+                        : knn_stream<K, R, false>(top, sm, g, qx, qy, qz, active, -1, INFINITY);
     double ex[K];
-    near_finalize<K>(top, g.pts, qx, qy, qz, ex);
+    ks_finalize<K>(top, g.pts, qx, qy, qz, ex);
     if (active && ok) {
         int32_t* row = idx_out + qi * k;
 #pragma unroll
         for (int a = 0; a < K; ++a)
             if (a < k) {
-                row[a] = __float_as_int(top.d[a]);
+                row[a] = __float_as_int(__ldg(&g.pts[max(top.id[a], 0)].w));
                 if (d2_out) d2_out[qi * k + a] = (float)ex[a];
             }
     }
-    fix_append(active && !ok, (int)t, fix_list, fix_count);
+    fix_append(active && !ok, (int)t, fail_list, fail_count);
+}
+
+template <int K>
+__global__ void __launch_bounds__(KsCfg<1>::THREADS, K <= 16 ? 5 : 1) knn_fast_kernel(GridView g, const float* __restrict__ query, const int32_t* __restrict__ qorder,
+                                                                     int64_t m, int k, int skip_self, int32_t* __restrict__ idx_out,
+                                                                     float* __restrict__ d2_out, int32_t* __restrict__ fail_list,
+                                                                     int32_t* __restrict__ fail_count) {
+    __shared__ KsShared<1> sm;
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    knn_fast_body<K, 1>(sm, g, query, qorder, t, t < m, k, skip_self, idx_out, d2_out, fail_list, fail_count);
+}
+
+// tier 2: the queries tier 1 listed, over the 5x5x5 block
+template <int K>
+__global__ void __launch_bounds__(KsCfg<2>::THREADS) knn_wide_kernel(GridView g, const float* __restrict__ query, const int32_t* __restrict__ qorder,
+                                                                     int k, int skip_self, int32_t* __restrict__ idx_out, float* __restrict__ d2_out,
+                                                                     const int32_t* __restrict__ todo_list, const int32_t* __restrict__ todo_count,
+                                                                     int32_t* __restrict__ fail_list, int32_t* __restrict__ fail_count) {
+    __shared__ KsShared<2> sm;
+    const int cnt = *todo_count;
+    for (int base = blockIdx.x * blockDim.x; base < cnt; base += gridDim.x * blockDim.x) {
+        const int i = base + threadIdx.x;
+        const bool active = i < cnt;
+        knn_fast_body<K, 2>(sm, g, query, qorder, active ? (int64_t)todo_list[i] : 0, active, k, skip_self, idx_out, d2_out, fail_list, fail_count);
+    }
 }
 
 // exact shell search for the listed queries
@@ -141,12 +162,16 @@ static void launch_knn(const ngpd_grid* G, const float* query, const int32_t* or
 template <int K>
 static int launch_knn_fast(const ngpd_grid* G, const float* query, const int32_t* order, int64_t m, int k, int skip, int32_t* idx, float* d2,
                            cudaStream_t s) {
+    // two fail lists (tier 1 -> tier 2 -> exact search) and their counters
     int32_t* fix = nullptr;
-    NGPD_CUDA_OK(cudaMallocAsync(&fix, (size_t)(m + 1) * sizeof(int32_t), s));
-    NGPD_CUDA_OK(cudaMemsetAsync(fix + m, 0, sizeof(int32_t), s));
-    knn_fast_kernel<K><<<(unsigned)cdiv(m, KF_THREADS), KF_THREADS, 0, s>>>(G->v, query, order, m, k, skip, idx, d2, fix, fix + m);
+    NGPD_CUDA_OK(cudaMallocAsync(&fix, (size_t)(2 * m + 2) * sizeof(int32_t), s));
+    int32_t *list1 = fix, *list2 = fix + m, *cnt1 = fix + 2 * m, *cnt2 = fix + 2 * m + 1;
+    NGPD_CUDA_OK(cudaMemsetAsync(cnt1, 0, 2 * sizeof(int32_t), s));
+    knn_fast_kernel<K><<<(unsigned)cdiv(m, KsCfg<1>::THREADS), KsCfg<1>::THREADS, 0, s>>>(G->v, query, order, m, k, skip, idx, d2, list1, cnt1);
+    int wide = (int)std::min<int64_t>(cdiv(m, KsCfg<2>::THREADS), (int64_t)num_sms() * 16);
+    knn_wide_kernel<K><<<wide, KsCfg<2>::THREADS, 0, s>>>(G->v, query, order, k, skip, idx, d2, list1, cnt1, list2, cnt2);
     int blocks = (int)std::min<int64_t>(cdiv(m, 128), (int64_t)num_sms() * 8);
-    knn_fix_kernel<K><<<blocks, 128, 0, s>>>(G->v, query, order, k, skip, idx, d2, fix, fix + m);
+    knn_fix_kernel<K><<<blocks, 128, 0, s>>>(G->v, query, order, k, skip, idx, d2, list2, cnt2);
     NGPD_CUDA_OK(cudaGetLastError());
     NGPD_CUDA_OK(cudaFreeAsync(fix, s));
     return 0;

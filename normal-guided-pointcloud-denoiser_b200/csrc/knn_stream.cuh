@@ -1,0 +1,270 @@
+// Fast path of the k-NN search (kernel group 2): per-lane candidate streams + sorting-network selection.
+//
+// One query per thread.  A query only ever needs the points of the 3x3x3 block of cells around its own cell (checked
+// afterwards; the rare query whose k-th neighbour lies outside goes to the exact shell search of knn.cuh), and in the
+// sorted point array that block is at most 18 contiguous ranges (9 cell rows along x, each split at most once by a
+// brick boundary).  The kernel therefore runs in three phases:
+//   1. ranges   every lane looks its ranges up in the two-level grid and parks them in shared memory (core row first);
+//   2. stream   a flat, warp-uniform loop: each lane walks ITS OWN ranges four candidates at a time.  Lanes are
+//               neighbours in tree order, so the lanes of one cell walk the same addresses (one L1 wavefront per
+//               distinct cell, 5-6 per warp) while no lane evaluates candidates of somebody else's block
+//               (the previous warp-union walk evaluated ~300 candidates per lane for ~80 useful ones).
+//               A candidate is turned into ONE 32-bit key: the fp32 squared distance with its 11 low mantissa bits
+//               replaced by (range slot, offset in range).  Keys below the lane's current threshold are appended
+//               to a 16-entry batch in shared memory; nothing is inserted one by one.
+//   3. select   whenever some lane's batch is nearly full, every lane sorts its batch with Batcher's odd-even merge
+//               network (63 compare-exchanges, 2 instructions each since a key carries its own id) and merges it
+//               into its sorted top-k with a bitonic half-cleaner + merge.  All lanes do the same thing at the same
+//               time: no divergence, no per-candidate insertion chains (ncu on the previous insertion kernel:
+//               10 of 32 lanes active in 34 % of its instructions).
+// Exactness is kept without fp64 in the inner loop:
+//   * keys order candidates by distance to 12 mantissa bits; a lane remembers the smallest key it ever dropped, and
+//     unless that is clearly (3e-4 relative: key truncation 2.4e-4 + fp32 evaluation error) above its k-th kept key
+//     and the k-th distance lies inside the lane's own 3x3x3 block, the query is put on a fix-up list and redone by
+//     the exact shell search;
+//   * the k survivors are re-evaluated in fp64 ((dx^2+dy^2)+dz^2, SciPy's order) and sorted by (distance, original
+//     index) before they are written.
+// A query answered here therefore has exactly the rows the exact kernel would give.
+//
+// The search is a template on the block radius R.  R = 1 (3x3x3 cells, 128 threads) answers ~97.5 % of the queries of
+// a surface cloud; its failures are compacted into a list and retried with R = 2 (5x5x5 cells, 64 threads per block
+// because of the 50 range slots per lane), and only what fails there too (isolated points, k-th neighbour farther than
+// two cells) reaches the one-query-per-thread exact shell search.  ncu on the first version, whose failures all
+// went to the exact search: that kernel took half as long as the fast kernel for 2.4 % of the queries.
+#pragma once
+#include "knn.cuh"
+
+namespace ngpd {
+
+constexpr int KS_BATCH = 16;          // keys per lane between two selection rounds
+constexpr int KS_GROUP = 4;           // candidates per inner step (loads in flight); the point array is padded by KS_GROUP
+constexpr int KS_OFFBITS = 6;         // a range slot holds at most 64 points (longer ranges take several slots)
+constexpr unsigned FULL = 0xffffffffu;
+
+template <int R>
+struct KsCfg {
+    static constexpr int ROWS = (2 * R + 1) * (2 * R + 1);
+    static constexpr int SLOTS = 2 * ROWS;                       // a row of 2R+1 <= 8 cells crosses at most one brick boundary
+    static constexpr int SLOTBITS = R == 1 ? 5 : 6;
+    static constexpr unsigned IDMASK = (1u << (SLOTBITS + KS_OFFBITS)) - 1u;
+    static constexpr int THREADS = R == 1 ? 128 : 64;
+    static constexpr double MARGIN = R == 1 ? 3e-4 : 6e-4;       // key truncation (2^-12 / 2^-11) + fp32 evaluation error
+};
+
+template <int R>
+struct KsShared {
+    int2 rng[KsCfg<R>::SLOTS][KsCfg<R>::THREADS];   // (first point, one past the last) of each slot
+    float batch[KS_BATCH][KsCfg<R>::THREADS];
+};
+
+__device__ __forceinline__ void ks_ce(float& a, float& b) {
+    float lo = fminf(a, b), hi = fmaxf(a, b);
+    a = lo; b = hi;
+}
+
+// Batcher's odd-even merge sort, fully unrolled: every index is a compile-time constant
+template <int N>
+__device__ __forceinline__ void ks_sort(float (&a)[N]) {
+#pragma unroll
+    for (int p = 1; p < N; p *= 2)
+#pragma unroll
+        for (int k = p; k >= 1; k /= 2)
+#pragma unroll
+            for (int j = k % p; j <= N - 1 - k; j += 2 * k)
+#pragma unroll
+                for (int i = 0; i < k; ++i)
+                    if (i + j + k < N && (i + j) / (2 * p) == (i + j + k) / (2 * p)) ks_ce(a[i + j], a[i + j + k]);
+}
+
+// ascending sort of a bitonic sequence
+template <int N>
+__device__ __forceinline__ void ks_bitonic_merge(float (&a)[N]) {
+#pragma unroll
+    for (int k = N / 2; k >= 1; k /= 2)
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            if ((i & k) == 0) ks_ce(a[i], a[i | k]);
+}
+
+template <int K>
+struct KsTop {
+    float key[K];     // ascending
+    int id[K];        // filled by the decode step
+};
+
+// one selection round: the lane's batch (cnt keys in shared memory) is merged into its top-k
+template <int K, int R>
+__device__ __forceinline__ void ks_round(KsTop<K>& t, KsShared<R>& sm, int cnt, float& rej) {
+    const int tid = threadIdx.x;
+    float b[KS_BATCH];
+#pragma unroll
+    for (int i = 0; i < KS_BATCH; ++i) { float v = sm.batch[i][tid]; b[i] = i < cnt ? v : INFINITY; }
+    ks_sort<KS_BATCH>(b);
+    constexpr int M = K < KS_BATCH ? K : KS_BATCH;
+    // top (ascending) against the batch (descending): the minima are the k smallest of both and form a bitonic sequence
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        float lo = fminf(t.key[K - 1 - i], b[i]), hi = fmaxf(t.key[K - 1 - i], b[i]);
+        t.key[K - 1 - i] = lo;
+        rej = fminf(rej, hi);
+    }
+    ks_bitonic_merge<K>(t.key);
+    if (K < KS_BATCH) rej = fminf(rej, b[K < KS_BATCH ? K : 0]);
+}
+
+// Search of the (2R+1)^3 block of cells around the lane's own cell.  Returns true when t.id[] holds the lane's final
+// neighbours (tree positions, still in key order); false = hand the query to the next tier.
+template <int K, int R, bool SELF>
+__device__ __forceinline__ bool knn_stream(KsTop<K>& t, KsShared<R>& sm, const GridView& g, float qx, float qy, float qz,
+                                           bool active, int self_orig, float bound) {
+    using C = KsCfg<R>;
+    const int tid = threadIdx.x;
+    const double rx = (double)qx - g.ox, ry = (double)qy - g.oy, rz = (double)qz - g.oz;
+    const int cx = min(max((int)floor(rx * g.inv_h), 0), g.nx - 1);
+    const int cy = min(max((int)floor(ry * g.inv_h), 0), g.ny - 1);
+    const int cz = min(max((int)floor(rz * g.inv_h), 0), g.nz - 1);
+
+    // ---- phase 1: the block's point ranges, the lane's own row first
+    int nr = 0;
+    bool over = false;
+    if (active) {
+        const int xa = max(cx - R, 0), xb = min(cx + R, g.nx - 1);
+        constexpr int W = 2 * R + 1, MID = (C::ROWS - 1) / 2;
+#pragma unroll(R == 1 ? 9 : 1)
+        for (int tt = 0; tt < C::ROWS; ++tt) {
+            const int o = tt == 0 ? MID : (tt <= MID ? tt - 1 : tt);      // (dy 0, dz 0) first
+            const int y = cy + (o % W) - R, z = cz + (o / W) - R;
+            if ((unsigned)y >= (unsigned)g.ny || (unsigned)z >= (unsigned)g.nz) continue;
+            const int64_t trow = ((int64_t)(z >> 3) * g.tby + (y >> 3)) * g.tbx;
+            const int lrow = ((z & 7) << 6) | ((y & 7) << 3);
+            int x0 = xa;
+#pragma unroll
+            for (int piece = 0; piece < 2; ++piece) {
+                if (x0 > xb) break;
+                const int xe = min(xb, x0 | 7);
+                const int b = __ldg(g.top + trow + (x0 >> 3));
+                if (b >= 0) {
+                    const int* f = g.fine + (int64_t)b * 513 + lrow;
+                    int s = __ldg(f + (x0 & 7));
+                    const int e = __ldg(f + (xe & 7) + 1);
+                    while (s < e) {                                    // one slot per 64 points
+                        const int ee = min(e, s + (1 << KS_OFFBITS));
+                        if (nr < C::SLOTS) { sm.rng[nr][tid] = make_int2(s, ee); ++nr; } else over = true;
+                        s = ee;
+                    }
+                }
+                x0 = xe + 1;
+            }
+        }
+    }
+
+    // ---- phase 2 + 3: stream the ranges four candidates at a time, select in rounds
+#pragma unroll
+    for (int a = 0; a < K; ++a) t.key[a] = INFINITY;
+    float tau = bound, rej = INFINITY;
+    const float4* pp = g.pts;
+    int rem = 0, r = 0;
+    unsigned idv = 0;
+    float* const b0 = &sm.batch[0][tid];
+    float* bp = b0;
+    if (nr > 0) { int2 q = sm.rng[0][tid]; pp = g.pts + q.x; rem = q.y - q.x; r = 1; }
+    while (__any_sync(FULL, rem > 0)) {
+        float4 p[KS_GROUP];
+#pragma unroll
+        for (int u = 0; u < KS_GROUP; ++u) p[u] = __ldg(pp + u);       // may run past the range: the array is padded, `rem` masks
+#pragma unroll
+        for (int u = 0; u < KS_GROUP; ++u) {
+            float dx = p[u].x - qx, dy = p[u].y - qy, dz = p[u].z - qz;
+            float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            bool valid = u < rem;
+            if (SELF) valid = valid && (__float_as_int(p[u].w) != self_orig);
+            float key = valid ? __uint_as_float((__float_as_uint(d2) & ~C::IDMASK) | (idv + u)) : INFINITY;
+            bool take = key < tau;
+            if (take) { *bp = key; bp += C::THREADS; }
+            rej = fminf(rej, take ? INFINITY : key);
+        }
+        rem -= KS_GROUP;
+        if (rem > 0) { pp += KS_GROUP; idv += KS_GROUP; }
+        else if (r < nr) { int2 q = sm.rng[r][tid]; pp = g.pts + q.x; rem = q.y - q.x; idv = (unsigned)r << KS_OFFBITS; ++r; }
+        else { pp = g.pts; rem = 0; }                                   // done: keep the speculative loads in bounds
+        if (__any_sync(FULL, bp > b0 + (KS_BATCH - KS_GROUP) * C::THREADS)) {
+            ks_round<K, R>(t, sm, (int)(bp - b0) / C::THREADS, rej);
+            bp = b0;
+            tau = fminf(bound, t.key[K - 1]);
+        }
+    }
+    if (__any_sync(FULL, bp > b0)) ks_round<K, R>(t, sm, (int)(bp - b0) / C::THREADS, rej);
+
+    // ---- decode the survivors' ids
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+        unsigned bits = __float_as_uint(t.key[a]);
+        bool real = t.key[a] < INFINITY;
+        int slot = min((int)((bits & C::IDMASK) >> KS_OFFBITS), C::SLOTS - 1);
+        t.id[a] = real ? sm.rng[slot][tid].x + (int)(bits & ((1u << KS_OFFBITS) - 1u)) : -1;
+    }
+    if (!active || over) return false;
+    // the lane saw every point of its block: final iff the list is full, its k-th distance lies inside the block, and
+    // no dropped candidate is within the key resolution of it
+    const float worst = __uint_as_float(__float_as_uint(t.key[K - 1]) & ~C::IDMASK);
+    const float rejt = __uint_as_float(__float_as_uint(rej) & ~C::IDMASK);
+    double reach = DBL_MAX;
+    if (cx - R > 0) reach = fmin(reach, rx - (double)(cx - R) * g.h);
+    if (cx + R < g.nx - 1) reach = fmin(reach, (double)(cx + R + 1) * g.h - rx);
+    if (cy - R > 0) reach = fmin(reach, ry - (double)(cy - R) * g.h);
+    if (cy + R < g.ny - 1) reach = fmin(reach, (double)(cy + R + 1) * g.h - ry);
+    if (cz - R > 0) reach = fmin(reach, rz - (double)(cz - R) * g.h);
+    if (cz + R < g.nz - 1) reach = fmin(reach, (double)(cz + R + 1) * g.h - rz);
+    const double wmax = (double)worst * (1.0 + C::MARGIN);
+    const double rr = reach - g.h * 1e-9;
+    const bool inside = (reach == DBL_MAX) ? true : (rr > 0.0 && wmax < rr * rr);
+    const bool clear = (double)rejt > wmax;
+    return t.key[K - 1] < INFINITY && inside && clear;
+}
+
+// exact re-evaluation and ordering of the k kept candidates: (fp64 distance, original index).  On return t.id[] are
+// tree positions in final order and ex[] the fp64 squared distances.  (Original indices only matter between candidates
+// at exactly the same distance; they are fetched on demand.)
+template <int K>
+__device__ __forceinline__ void ks_finalize(KsTop<K>& t, const float4* __restrict__ pts, float qx, float qy, float qz, double (&ex)[K]) {
+    const double dqx = (double)qx, dqy = (double)qy, dqz = (double)qz;
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+        int j = t.id[a];
+        float4 p = __ldg(pts + max(j, 0));
+        double dx = dqx - (double)p.x, dy = dqy - (double)p.y, dz = dqz - (double)p.z;
+        ex[a] = j >= 0 ? __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)) : DBL_MAX;
+    }
+    // nearly sorted already (key order): odd-even transposition passes until nothing moves anywhere in the warp
+    bool moved = true;
+    while (__any_sync(FULL, moved)) {
+        moved = false;
+#pragma unroll
+        for (int par = 0; par < 2; ++par) {
+#pragma unroll
+            for (int a = par; a + 1 < K; a += 2) {
+                bool sw = ex[a + 1] < ex[a];
+                if (ex[a + 1] == ex[a] && t.id[a] >= 0 && t.id[a + 1] >= 0)
+                    sw = __float_as_int(__ldg(&pts[t.id[a + 1]].w)) < __float_as_int(__ldg(&pts[t.id[a]].w));
+                if (sw) {
+                    double td = ex[a]; ex[a] = ex[a + 1]; ex[a + 1] = td;
+                    int tj = t.id[a]; t.id[a] = t.id[a + 1]; t.id[a + 1] = tj;
+                    moved = true;
+                }
+            }
+        }
+    }
+}
+
+// warp-aggregated append of the lanes with `flag` to a global list
+__device__ __forceinline__ void fix_append(bool flag, int value, int32_t* __restrict__ list, int32_t* __restrict__ count) {
+    unsigned m = __ballot_sync(FULL, flag);
+    if (!m) return;
+    int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == __ffs(m) - 1) base = atomicAdd(count, __popc(m));
+    base = __shfl_sync(FULL, base, __ffs(m) - 1);
+    if (flag) list[base + __popc(m & ((1u << lane) - 1u))] = value;
+}
+
+}  // namespace ngpd

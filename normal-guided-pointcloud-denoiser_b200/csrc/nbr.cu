@@ -18,14 +18,19 @@ __device__ __forceinline__ RowSpan row_span(int64_t r, const int32_t* idx, const
 }
 
 __global__ void __launch_bounds__(128) pca_kernel(Packed3 pos, const int32_t* __restrict__ idx, const int32_t* __restrict__ offsets,
-                                                  int64_t m, int k, float* __restrict__ normals, float* __restrict__ eigval) {
+                                                  int64_t m, int k, float* __restrict__ normals, float* __restrict__ eigval,
+                                                  float* __restrict__ eigvec) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= m) return;
     RowSpan s = row_span(r, idx, offsets, nullptr, k);
     float w[3], V[9];
     pca_point(pos, s.nbr, s.cnt, w, V);
-    normals[3 * r] = V[0]; normals[3 * r + 1] = V[3]; normals[3 * r + 2] = V[6];
+    if (normals) { normals[3 * r] = V[0]; normals[3 * r + 1] = V[3]; normals[3 * r + 2] = V[6]; }
     if (eigval) { eigval[3 * r] = w[0]; eigval[3 * r + 1] = w[1]; eigval[3 * r + 2] = w[2]; }
+    if (eigvec) {
+#pragma unroll
+        for (int c = 0; c < 9; ++c) eigvec[9 * r + c] = V[c];
+    }
 }
 
 __global__ void __launch_bounds__(128) nvt_kernel(Packed3 pos, Packed3 nrm, const int32_t* __restrict__ idx, const int32_t* __restrict__ offsets,
@@ -153,10 +158,10 @@ static inline unsigned strided_grid(int64_t n, int threads) {
 using namespace ngpd;
 
 extern "C" __attribute__((visibility("default"))) int ngpd_pca_normals(const float* pos, const int32_t* idx, const int32_t* offsets, int64_t m, int k,
-                                float* normals_out, float* eigval_out, void* stream) {
-    NGPD_REQUIRE(pos && idx && normals_out, "ngpd_pca_normals: NULL argument");
+                                float* normals_out, float* eigval_out, float* eigvec_out, void* stream) {
+    NGPD_REQUIRE(pos && idx && (normals_out || eigvec_out), "ngpd_pca_normals: NULL argument");
     if (m <= 0) return 0;
-    pca_kernel<<<grid_for(m, 128), 128, 0, (cudaStream_t)stream>>>(Packed3{pos}, idx, offsets, m, k, normals_out, eigval_out);
+    pca_kernel<<<grid_for(m, 128), 128, 0, (cudaStream_t)stream>>>(Packed3{pos}, idx, offsets, m, k, normals_out, eigval_out, eigvec_out);
     NGPD_CUDA_OK(cudaGetLastError());
     return 0;
 }

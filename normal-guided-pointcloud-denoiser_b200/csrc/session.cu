@@ -10,7 +10,7 @@
 // another GPU, refreshed between phases by ngpd_session_{export,import}_rows.
 #include <vector>
 #include <algorithm>
-#include "knn_fast.cuh"
+#include "knn_stream.cuh"
 #include "point_math.cuh"
 #include "../../include/ngpd.h"
 
@@ -77,33 +77,60 @@ __global__ void __launch_bounds__(128) session_knn_kernel(GridView g, const floa
         if (a < k) row[a] = top.id[a] >= 0 ? top.id[a] : (int32_t)s;   // fewer than k tree points: pad with self
 }
 
-template <int K>
-__global__ void __launch_bounds__(KF_THREADS) session_knn_fast_kernel(GridView g, const float4* __restrict__ pos, const uint8_t* __restrict__ owned,
-                                                                      int64_t n, int k, int32_t* __restrict__ idx, int32_t* __restrict__ fix_list,
-                                                                      int32_t* __restrict__ fix_count, const float* __restrict__ rk_in,
-                                                                      float* __restrict__ moved, float* __restrict__ rk_out) {
-    __shared__ KfShared sm;
-    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool active = s < n && (!owned || owned[s]);
+// tier 1 (R = 1, every row) and tier 2 (R = 2, the rows tier 1 listed) of the streaming search
+template <int K, int R>
+__device__ __forceinline__ void session_knn_body(KsShared<R>& sm, const GridView& g, const float4* __restrict__ pos, int64_t s, bool active,
+                                                 int k, int32_t* __restrict__ idx, int32_t* __restrict__ fail_list, int32_t* __restrict__ fail_count,
+                                                 const float* __restrict__ rk_in, float* __restrict__ moved, float* __restrict__ rk_out) {
     float4 q = active ? __ldg(pos + s) : make_float4(0.f, 0.f, 0.f, 0.f);
     float bound = INFINITY;
     if (active && rk_in) {
         float r = sqrtf(rk_in[s]) + moved[s];
-        bound = r * r * 1.00001f;                 // > (sqrt(rk) + moved)^2 whatever the fp32 roundings above did
+        bound = r * r * 1.002f;                   // > (sqrt(rk) + moved)^2 by more than the keys' resolution
     }
-    Near<K> top;
-    top.init(bound);
-    bool ok = knn_lockstep<K, false>(top, sm, g, q.x, q.y, q.z, active, -1);
+    KsTop<K> top;
+    bool ok = knn_stream<K, R, false>(top, sm, g, q.x, q.y, q.z, active, -1, bound);
     double ex[K];
-    near_finalize<K>(top, g.pts, q.x, q.y, q.z, ex);
+    ks_finalize<K>(top, g.pts, q.x, q.y, q.z, ex);
     if (active && ok) {
-        int32_t* row = idx + s * k;
+        if (k == K) {
+            int4* row = reinterpret_cast<int4*>(idx + s * K);
 #pragma unroll
-        for (int a = 0; a < K; ++a)
-            if (a < k) row[a] = top.id[a];
+            for (int a = 0; a < K / 4; ++a) row[a] = make_int4(top.id[4 * a], top.id[4 * a + 1], top.id[4 * a + 2], top.id[4 * a + 3]);
+        } else {
+#pragma unroll
+            for (int a = 0; a < K; ++a)
+                if (a < k) idx[s * k + a] = top.id[a];
+        }
         if (rk_out) { rk_out[s] = __double2float_ru(ex[K - 1]); moved[s] = 0.0f; }
     }
-    fix_append(active && !ok, (int)s, fix_list, fix_count);
+    fix_append(active && !ok, (int)s, fail_list, fail_count);
+}
+
+template <int K>
+__global__ void __launch_bounds__(KsCfg<1>::THREADS, K <= 16 ? 5 : 1) session_knn_fast_kernel(GridView g, const float4* __restrict__ pos, const uint8_t* __restrict__ owned,
+                                                                             int64_t n, int k, int32_t* __restrict__ idx, int32_t* __restrict__ fail_list,
+                                                                             int32_t* __restrict__ fail_count, const float* __restrict__ rk_in,
+                                                                             float* __restrict__ moved, float* __restrict__ rk_out) {
+    __shared__ KsShared<1> sm;
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool active = s < n && (!owned || owned[s]);
+    session_knn_body<K, 1>(sm, g, pos, s, active, k, idx, fail_list, fail_count, rk_in, moved, rk_out);
+}
+
+template <int K>
+__global__ void __launch_bounds__(KsCfg<2>::THREADS) session_knn_wide_kernel(GridView g, const float4* __restrict__ pos, int k, int32_t* __restrict__ idx,
+                                                                             const int32_t* __restrict__ todo_list, const int32_t* __restrict__ todo_count,
+                                                                             int32_t* __restrict__ fail_list, int32_t* __restrict__ fail_count,
+                                                                             const float* __restrict__ rk_in, float* __restrict__ moved,
+                                                                             float* __restrict__ rk_out) {
+    __shared__ KsShared<2> sm;
+    const int cnt = *todo_count;
+    for (int base = blockIdx.x * blockDim.x; base < cnt; base += gridDim.x * blockDim.x) {
+        const int i = base + threadIdx.x;
+        const bool active = i < cnt;
+        session_knn_body<K, 2>(sm, g, pos, active ? (int64_t)todo_list[i] : 0, active, k, idx, fail_list, fail_count, rk_in, moved, rk_out);
+    }
 }
 
 template <int K>
@@ -125,7 +152,21 @@ __global__ void __launch_bounds__(128) session_knn_fix_kernel(GridView g, const 
     }
 }
 
+// neighbour row of point s in registers: K > 0 = compile-time row length (16-byte vector loads, fully unrolled
+// consumers), K = 0 = runtime length read through the pointer
+template <int K>
+struct RowRegs {
+    int32_t v[K > 0 ? K : 1];
+    __device__ __forceinline__ int64_t operator()(int a) const { return (int64_t)v[a]; }
+    __device__ __forceinline__ void load(const int32_t* __restrict__ row) {
+        const int4* r4 = reinterpret_cast<const int4*>(row);
+#pragma unroll
+        for (int a = 0; a < K / 4; ++a) { int4 q = __ldg(r4 + a); v[4 * a] = q.x; v[4 * a + 1] = q.y; v[4 * a + 2] = q.z; v[4 * a + 3] = q.w; }
+    }
+};
+
 // stage 1: filtered NVT on the current normals, smoothed normal out
+template <int K>
 __global__ void __launch_bounds__(128) session_nvt_smooth_kernel(Quad4 pos, Quad4 nrm, const uint8_t* __restrict__ owned,
                                                                  const int32_t* __restrict__ idx, int64_t n, int k, float x_thresh,
                                                                  float tau, float damp, float4* __restrict__ fn) {
@@ -133,12 +174,19 @@ __global__ void __launch_bounds__(128) session_nvt_smooth_kernel(Quad4 pos, Quad
     if (s >= n) return;
     if (owned && !owned[s]) return;
     NvtResult o;
-    nvt_point(pos, nrm, s, idx + s * k, k, x_thresh, o, nullptr);
+    if (K > 0) {
+        RowRegs<K> row;
+        row.load(idx + s * K);
+        nvt_point_row<K>(pos, nrm, s, row, idx + s * K, K, x_thresh, o, nullptr);
+    } else {
+        nvt_point(pos, nrm, s, idx + s * k, k, x_thresh, o, nullptr);
+    }
     V3 f = smooth_normal(o.w, o.V, nrm(s), tau, damp);
     fn[s] = make_float4(f.x, f.y, f.z, 0.0f);
 }
 
 // stage 2: filtered NVT on the smoothed normals, label + crease direction out
+template <int K>
 __global__ void __launch_bounds__(128) session_nvt_classify_kernel(Quad4 pos, Quad4 fn, const uint8_t* __restrict__ owned,
                                                                    const int32_t* __restrict__ idx, int64_t n, int k, float x_thresh,
                                                                    float scale, uint8_t* __restrict__ label, float4* __restrict__ edge) {
@@ -146,7 +194,13 @@ __global__ void __launch_bounds__(128) session_nvt_classify_kernel(Quad4 pos, Qu
     if (s >= n) return;
     if (owned && !owned[s]) return;
     NvtResult o;
-    nvt_point(pos, fn, s, idx + s * k, k, x_thresh, o, nullptr);
+    if (K > 0) {
+        RowRegs<K> row;
+        row.load(idx + s * K);
+        nvt_point_row<K>(pos, fn, s, row, idx + s * K, K, x_thresh, o, nullptr);
+    } else {
+        nvt_point(pos, fn, s, idx + s * k, k, x_thresh, o, nullptr);
+    }
     label[s] = (uint8_t)classify(o.w, scale);
     edge[s] = make_float4(o.V[0], o.V[3], o.V[6], 0.0f);
 }
@@ -276,13 +330,16 @@ template <int K>
 static void run_knn_fast(ngpd_session* S, int k, int32_t* idx, cudaStream_t st, bool track) {
     const GridView& g = S->grid->v;
     const float4* p = S->pos[S->cur];
-    int32_t* cnt = S->fix + S->n;
-    cudaMemsetAsync(cnt, 0, sizeof(int32_t), st);
+    // fix = [tier-1 fail list (n) | tier-2 fail list (n) | two counters]
+    int32_t *list1 = S->fix, *list2 = S->fix + S->n, *cnt1 = S->fix + 2 * S->n, *cnt2 = cnt1 + 1;
+    cudaMemsetAsync(cnt1, 0, 2 * sizeof(int32_t), st);
     const float* rk_in = (track && S->bound_k == K && S->use_bound) ? S->rk : nullptr;
     float* rk_out = track ? S->rk : nullptr;
-    session_knn_fast_kernel<K><<<(unsigned)cdiv(S->n, KF_THREADS), KF_THREADS, 0, st>>>(g, p, S->owned, S->n, k, idx, S->fix, cnt, rk_in, S->moved, rk_out);
+    session_knn_fast_kernel<K><<<(unsigned)cdiv(S->n, KsCfg<1>::THREADS), KsCfg<1>::THREADS, 0, st>>>(g, p, S->owned, S->n, k, idx, list1, cnt1, rk_in, S->moved, rk_out);
+    int wide = (int)std::min<int64_t>(cdiv(S->n, KsCfg<2>::THREADS), (int64_t)num_sms() * 16);
+    session_knn_wide_kernel<K><<<wide, KsCfg<2>::THREADS, 0, st>>>(g, p, k, idx, list1, cnt1, list2, cnt2, rk_in, S->moved, rk_out);
     int blocks = (int)std::min<int64_t>(cdiv(S->n, 128), (int64_t)num_sms() * 8);
-    session_knn_fix_kernel<K><<<blocks, 128, 0, st>>>(g, p, k, idx, S->fix, cnt, S->moved, rk_out);
+    session_knn_fix_kernel<K><<<blocks, 128, 0, st>>>(g, p, k, idx, list2, cnt2, S->moved, rk_out);
     if (track) S->bound_k = K;
 }
 
@@ -337,7 +394,7 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_create(const 
     if (e == cudaSuccess) e = cudaMalloc(&S->label, (size_t)n);
     if (e == cudaSuccess) e = cudaMalloc(&S->acc, 4 * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&S->cd, 4 * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc(&S->fix, ((size_t)n + 1) * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&S->fix, (2 * (size_t)n + 2) * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMalloc(&S->rk, (size_t)n * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&S->moved, (size_t)n * sizeof(float));
     if (e != cudaSuccess) { set_error("ngpd_session_create: %s", cudaGetErrorString(e)); ngpd_session_destroy(S); return -2; }
@@ -399,11 +456,19 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_phase_feature
         { ProfScope ps(S, st, 0); rc = run_knn(S, kf, S->idx, st, true); }
         if (rc) return rc;
         { ProfScope ps(S, st, 1);
-          session_nvt_smooth_kernel<<<b, 128, 0, st>>>(pos, Quad4{S->nrm}, S->owned, S->idx, S->n, kf, p->x_thresh, p->tau, p->damp, S->fn); }
-        S->launches += S->exact_only ? 2 : 3;
+          Quad4 nq{S->nrm};
+          if (kf == 16) session_nvt_smooth_kernel<16><<<b, 128, 0, st>>>(pos, nq, S->owned, S->idx, S->n, kf, p->x_thresh, p->tau, p->damp, S->fn);
+          else if (kf == 32) session_nvt_smooth_kernel<32><<<b, 128, 0, st>>>(pos, nq, S->owned, S->idx, S->n, kf, p->x_thresh, p->tau, p->damp, S->fn);
+          else if (kf == 8) session_nvt_smooth_kernel<8><<<b, 128, 0, st>>>(pos, nq, S->owned, S->idx, S->n, kf, p->x_thresh, p->tau, p->damp, S->fn);
+          else session_nvt_smooth_kernel<0><<<b, 128, 0, st>>>(pos, nq, S->owned, S->idx, S->n, kf, p->x_thresh, p->tau, p->damp, S->fn); }
+        S->launches += S->exact_only ? 2 : 4;
     } else {
         { ProfScope ps(S, st, 2);
-          session_nvt_classify_kernel<<<b, 128, 0, st>>>(pos, Quad4{S->fn}, S->owned, S->idx, S->n, kf, p->x_thresh, p->scale, S->label, S->edge); }
+          Quad4 fq{S->fn};
+          if (kf == 16) session_nvt_classify_kernel<16><<<b, 128, 0, st>>>(pos, fq, S->owned, S->idx, S->n, kf, p->x_thresh, p->scale, S->label, S->edge);
+          else if (kf == 32) session_nvt_classify_kernel<32><<<b, 128, 0, st>>>(pos, fq, S->owned, S->idx, S->n, kf, p->x_thresh, p->scale, S->label, S->edge);
+          else if (kf == 8) session_nvt_classify_kernel<8><<<b, 128, 0, st>>>(pos, fq, S->owned, S->idx, S->n, kf, p->x_thresh, p->scale, S->label, S->edge);
+          else session_nvt_classify_kernel<0><<<b, 128, 0, st>>>(pos, fq, S->owned, S->idx, S->n, kf, p->x_thresh, p->scale, S->label, S->edge); }
         S->launches += 1;
     }
     NGPD_CUDA_OK(cudaGetLastError());
@@ -425,7 +490,7 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_phase_flat_sc
     } else {
         session_center_kernel<<<1, 1, 0, st>>>(S->acc, S->cd);
         session_class_max_kernel<<<strided(S->n, 256), 256, 0, st>>>(pos, S->owned, S->label, key, S->idx, S->n, S->idx_k, p->k_update, S->cd);
-        S->launches += S->exact_only ? 2 : 3;
+        S->launches += 2;
     }
     NGPD_CUDA_OK(cudaGetLastError());
     return 0;
@@ -500,7 +565,7 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_set_knn_mode(
 extern "C" __attribute__((visibility("default"))) int ngpd_session_last_fixups(ngpd_session_t* S, void* stream_) {
     if (!S) return -1;
     int32_t c = 0;
-    if (cudaMemcpyAsync(&c, S->fix + S->n, sizeof(c), cudaMemcpyDeviceToHost, (cudaStream_t)stream_) != cudaSuccess) return -1;
+    if (cudaMemcpyAsync(&c, S->fix + 2 * S->n, sizeof(c), cudaMemcpyDeviceToHost, (cudaStream_t)stream_) != cudaSuccess) return -1;
     cudaStreamSynchronize((cudaStream_t)stream_);
     return c;
 }

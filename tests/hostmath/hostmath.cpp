@@ -6,6 +6,7 @@
 using std::signbit;
 using std::isfinite;
 #include "../../normal-guided-pointcloud-denoiser_b200/csrc/point_math.cuh"
+#include "eig3_generic.h"
 
 using namespace ngpd;
 
@@ -23,6 +24,14 @@ void hm_eigh3(const float* T, int64_t m, float* w, float* V) {
     }
 }
 
+// the array-indexed transcription of the LAPACK loops (cross-check for the n = 3 specialisation)
+void hm_eigh3_generic(const float* T, int64_t m, float* w, float* V) {
+    for (int64_t r = 0; r < m; ++r) {
+        const float* a = T + 9 * r;
+        ngpd_generic::eigh3_lapack(a[0], a[3], a[6], a[4], a[7], a[8], w + 3 * r, V + 9 * r);
+    }
+}
+
 void hm_nvt(const float* pos, const float* nrm, const int32_t* idx, const int32_t* rows, int64_t m, int k, float x_thresh,
             float* w, float* V, float* T, int32_t* sumw) {
     HostPacked3 P{pos}, N{nrm};
@@ -35,6 +44,18 @@ void hm_nvt(const float* pos, const float* nrm, const int32_t* idx, const int32_
         float* t = T + 9 * r;
         t[0] = t6[0]; t[1] = t6[1]; t[2] = t6[2]; t[3] = t6[1]; t[4] = t6[3]; t[5] = t6[4]; t[6] = t6[2]; t[7] = t6[4]; t[8] = t6[5];
         sumw[r] = o.sumw;
+    }
+}
+
+// neighbour-filter decision: the reference's exact sequence and the division-free shortcut, for the same edges
+void hm_weight(const float* vi, const float* vj, const float* nj, int64_t m, float x_thresh, uint8_t* exact, uint8_t* quick) {
+    HostPacked3 A{vi}, B{vj}, N{nj};
+    NvtThreshold th(x_thresh);
+    for (int64_t r = 0; r < m; ++r) {
+        exact[r] = nvt_weight(A(r), B(r), N(r), x_thresh);
+        bool certain = th.quick;
+        bool q = nvt_weight_quick(A(r), B(r), N(r), th, certain);
+        quick[r] = certain ? q : nvt_weight(A(r), B(r), N(r), x_thresh);
     }
 }
 

@@ -361,7 +361,8 @@ def test_denoise_vs_reference_free_running(ng, fandisk):
     assert (ang > 1e-4).mean() < 0.0675
     cd = ng.TorchUtils.ChamferDistance(cu(fandisk["gt"]), p.graph.pos).double().mean().item()
     ref = fandisk["cd_final"].mean(dtype=np.float64)
-    assert abs(cd - ref) / ref < 1e-3
+    # Chamfer yardstick (scripts/noise_floor.py, three 1-ulp trials): the reference differs from itself by 3.2e-4 .. 8.5e-4 relative
+    assert abs(cd - ref) / ref < 3e-3
 
 
 def test_session_labels_vs_reference(ng, fandisk):
@@ -408,7 +409,10 @@ def test_until_minimum_error_loop(ng, until_min):
     assert torch.equal(p.graph.pos, noisy)                                   # reset to the noisy input on exit
     scale = np.abs(until_min["pos0"]).max()
     err = np.abs(best.cpu().numpy() - until_min["pos_returned"]).max(axis=1) / scale
-    assert (err > 1e-5).mean() < 0.1257
+    # yardstick (scripts/noise_floor.py): the reference's algorithm differs from ITSELF on 23.9 - 24.5 % of the positions
+    # (> 1e-5, max 2.5e-3) after these three iterations when its input normals move by 1 ulp
+    print(f"returned positions >1e-5 from the reference's: {(err > 1e-5).mean():.4%} (max {err.max():.2e})")
+    assert (err > 1e-5).mean() < 0.239 and err.max() < 1e-2
 
 
 def test_generic_strategy_path(ng, fandisk):
@@ -487,3 +491,50 @@ def test_session_large_runs_and_is_deterministic(ng):
     assert torch.isfinite(pos).all() and torch.isfinite(fn).all()
     assert torch.allclose(fn.norm(dim=1), torch.ones(n, device="cuda"), atol=1e-4)
     assert int(lab.max()) <= 2
+
+
+def test_eigh3_device_equals_host_transcription(ng):
+    """ngpd_eigh3 on the GPU (n = 3 specialisation, branch-free correctly rounded division / square root inside the
+    safe exponent window, plain operators outside it) is bit-identical to the array-indexed LAPACK transcription compiled
+    for the host (tests/hostmath/eig3_generic.h)."""
+    import ctypes
+    import subprocess
+    from conftest import ROOT
+    hmdir = os.path.join(ROOT, "tests", "hostmath")
+    so = os.path.join(hmdir, "libhostmath.so")
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++", os.path.join(hmdir, "hostmath.cpp"), "-o", so], check=True)
+    hm = ctypes.CDLL(so)
+    rng = np.random.default_rng(5)
+    m = 300_000
+
+    def sym(a):
+        return (a + a.transpose(0, 2, 1)) / 2
+
+    def votes(k, spread):
+        base = rng.normal(size=(m, 1, 3)); base /= np.linalg.norm(base, axis=2, keepdims=True)
+        n = base + spread * rng.normal(size=(m, k, 3)); n /= np.linalg.norm(n, axis=2, keepdims=True)
+        n = n.astype(np.float32)
+        return np.einsum("mki,mkj->mij", n, n) / np.float32(k)
+
+    cases = {"general": sym(rng.normal(size=(m, 3, 3))), "votes_flat": votes(16, 0.05), "votes_noisy": votes(16, 0.5),
+             "votes_crease": (votes(8, 0.02) + votes(8, 0.02)) / 2, "votes_rank1": votes(1, 0.0), "votes_rank2": votes(2, 0.3),
+             "zero": np.zeros((4, 3, 3)), "identity": np.tile(np.eye(3), (4, 1, 1)),
+             "window_low": sym(rng.normal(size=(m, 3, 3))) * 2.0 ** -9, "window_high": sym(rng.normal(size=(m, 3, 3))) * 2.0 ** 7,
+             "tiny": sym(rng.normal(size=(m, 3, 3))) * 1e-20, "huge": sym(rng.normal(size=(m, 3, 3))) * 1e15}
+    ax = np.eye(3)[rng.integers(0, 3, (m, 16))] * rng.choice([-1, 1], (m, 16, 1))
+    cases["axis_aligned"] = np.einsum("mki,mkj->mij", ax, ax) / 16
+    mixed = sym(rng.normal(size=(m, 3, 3))); mixed[:, 1:, 1:] *= 1e-12; mixed[:, 0, 1:] *= 1e-7; mixed[:, 1:, 0] *= 1e-7
+    cases["mixed_scales"] = mixed
+    pts = rng.normal(size=(m, 12, 3)) * np.array([1, 1, 0.01]); pts -= pts.mean(1, keepdims=True)
+    cases["covariance"] = np.einsum("mki,mkj->mij", pts, pts)
+    lib = ng._lib.load()
+    for name, T in cases.items():
+        T = np.ascontiguousarray(T.astype(np.float32)); n = len(T)
+        w1 = np.zeros((n, 3), np.float32); V1 = np.zeros((n, 3, 3), np.float32)
+        hm.hm_eigh3_generic(T.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(n), w1.ctypes.data_as(ctypes.c_void_p), V1.ctypes.data_as(ctypes.c_void_p))
+        Td = cu(T); wd = torch.empty((n, 3), device="cuda"); Vd = torch.empty((n, 3, 3), device="cuda")
+        ng._lib.check(lib.ngpd_eigh3(Td.data_ptr(), n, wd.data_ptr(), Vd.data_ptr(), None), "eigh3")
+        w2, V2 = wd.cpu().numpy(), Vd.cpu().numpy()
+        bad = ~((w1.view(np.uint32) == w2.view(np.uint32)).all(1) & (V1.view(np.uint32) == V2.view(np.uint32)).all((1, 2)))
+        print(f"\n{name}: {bad.sum()} of {n} tensors differ from the host transcription")
+        assert bad.sum() == 0, name

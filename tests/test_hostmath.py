@@ -117,3 +117,66 @@ def test_eigh3_properties(hm):
     assert np.abs(np.einsum("nij,njk->nik", A, V) - V * w[:, None, :]).max() < 2e-5
     wr = np.linalg.eigvalsh(A.astype(np.float64))
     assert np.abs(w - wr).max() < 1e-5
+
+
+def test_eigh3_static_equals_generic_transcription(hm):
+    """The product's n = 3 specialisation (csrc/eig3.cuh: named registers, one sweep body for QL and QR) is
+    bit-identical to the array-indexed transcription of the LAPACK loops (tests/hostmath/eig3_generic.h) on
+    general, voting-tensor-like, rank-deficient, diagonal, structurally sparse, scaled and repeated-eigenvalue inputs."""
+    rng = np.random.default_rng(0)
+    m = 200_000
+
+    def sym(a):
+        return (a + a.transpose(0, 2, 1)) / 2
+
+    def votes(k, spread):
+        base = rng.normal(size=(m, 1, 3)); base /= np.linalg.norm(base, axis=2, keepdims=True)
+        n = base + spread * rng.normal(size=(m, k, 3)); n /= np.linalg.norm(n, axis=2, keepdims=True)
+        n = n.astype(np.float32)
+        return np.einsum("mki,mkj->mij", n, n) / np.float32(k)
+
+    cases = {"general": sym(rng.normal(size=(m, 3, 3))), "votes_flat": votes(16, 0.05), "votes_noisy": votes(16, 0.5),
+             "votes_rank1": votes(1, 0.0), "votes_rank2": votes(2, 0.3), "zero": np.zeros((4, 3, 3)), "identity": np.tile(np.eye(3), (4, 1, 1)),
+             "tiny": sym(rng.normal(size=(m, 3, 3))) * 1e-20, "huge": sym(rng.normal(size=(m, 3, 3))) * 1e15}
+    ax = np.eye(3)[rng.integers(0, 3, (m, 16))] * rng.choice([-1, 1], (m, 16, 1))
+    cases["axis_aligned"] = np.einsum("mki,mkj->mij", ax, ax) / 16
+    d = np.zeros((m, 3, 3)); d[:, 0, 0], d[:, 1, 1], d[:, 2, 2] = rng.normal(size=(3, m)); cases["diagonal"] = d
+    for name, (r, c) in {"a31_zero": (2, 0), "a21_zero": (1, 0), "a32_zero": (2, 1)}.items():
+        a = sym(rng.normal(size=(m, 3, 3))); a[:, r, c] = a[:, c, r] = 0; cases[name] = a
+    pts = rng.normal(size=(m, 12, 3)) * np.array([1, 1, 0.01]); pts -= pts.mean(1, keepdims=True)
+    cases["covariance"] = np.einsum("mki,mkj->mij", pts, pts)
+    q = np.linalg.qr(rng.normal(size=(m, 3, 3)))[0]
+    lam = np.stack([np.ones(m), np.ones(m), rng.uniform(0, 2, m)], 1)
+    cases["repeated"] = np.einsum("mij,mj,mkj->mik", q, lam, q)
+    for name, T in cases.items():
+        T = np.ascontiguousarray(T.astype(np.float32)); n = len(T)
+        w1 = np.zeros((n, 3), np.float32); V1 = np.zeros((n, 3, 3), np.float32); w2 = w1.copy(); V2 = V1.copy()
+        hm.hm_eigh3(P(T), ctypes.c_int64(n), P(w1), P(V1))
+        hm.hm_eigh3_generic(P(T), ctypes.c_int64(n), P(w2), P(V2))
+        assert np.array_equal(w1.view(np.uint32), w2.view(np.uint32)), name
+        assert np.array_equal(V1.view(np.uint32), V2.view(np.uint32)), name
+
+
+@pytest.mark.parametrize("thresh", [0.25881898403167725, 0.5, 0.9999, 1.0, 0.0, -1.0, 1e-4])
+def test_nvt_weight_shortcut_equals_exact_sequence(hm, thresh):
+    """The division-free neighbour filter gives the reference's 0/1 weight on random edges, on edges constructed to sit
+    within a few ulp of the threshold, on zero-length and tiny edges, and for degenerate thresholds."""
+    rng = np.random.default_rng(7)
+    m = 400_000
+    vi = rng.normal(size=(m, 3)).astype(np.float32)
+    dv = (rng.normal(size=(m, 3)) * 10.0 ** rng.uniform(-6, 1, (m, 1))).astype(np.float32)
+    nj = rng.normal(size=(m, 3)); nj /= np.linalg.norm(nj, axis=1, keepdims=True)
+    # second half: normals with |u.n| = thresh * (1 + tiny), i.e. decisions on the edge
+    h = m // 2
+    u = dv[h:].astype(np.float64); u /= np.maximum(np.linalg.norm(u, axis=1, keepdims=True), 1e-300)
+    t = rng.normal(size=(m - h, 3)); t -= (t * u).sum(1, keepdims=True) * u; t /= np.linalg.norm(t, axis=1, keepdims=True)
+    x = np.clip(abs(thresh) * (1 + rng.uniform(-3e-6, 3e-6, (m - h, 1))), 0, 1)
+    nj[h:] = x * u * rng.choice([-1, 1], (m - h, 1)) + np.sqrt(1 - x * x) * t
+    nj = nj.astype(np.float32)
+    dv[:50] = 0; dv[50:100] *= 1e-20
+    vj = (vi + dv).astype(np.float32)
+    ex = np.zeros(m, np.uint8); qk = np.zeros(m, np.uint8)
+    hm.hm_weight(P(vi), P(vj), P(nj), ctypes.c_int64(m), ctypes.c_float(thresh), P(ex), P(qk))
+    assert np.array_equal(ex, qk)
+    if 0 < thresh < 1:
+        assert 0.05 < ex[h:].mean() < 0.95          # the constructed edges really straddle the threshold
