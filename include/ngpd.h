@@ -143,6 +143,8 @@ int ngpd_session_get_profile(ngpd_session_t* s, double* ms_out, int32_t* launche
  * query.  Both give the same rows.  last_fixups = queries the last kNN pass handed to the exact search (synchronises). */
 int ngpd_session_set_knn_mode(ngpd_session_t* s, int mode);
 int ngpd_session_last_fixups(ngpd_session_t* s, void* stream);
+/* out2_host = {queries the 3x3x3 tier of the last kNN pass handed on, queries the 5x5x5 tier handed to the exact search} */
+int ngpd_session_knn_stats(ngpd_session_t* s, int32_t* out2_host, void* stream);
 /* number of kernels the last ngpd_session_step launched */
 int ngpd_session_launch_count(const ngpd_session_t* s);
 /* tree-order views for tests/benchmarks: perm (sorted -> original) */

@@ -59,6 +59,7 @@ SIGNATURES = {
     "ngpd_session_launch_count": (ctypes.c_int, [c_vp]),
     "ngpd_session_set_knn_mode": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "ngpd_session_last_fixups": (ctypes.c_int, [c_vp, c_vp]),
+    "ngpd_session_knn_stats": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i32), c_vp]),
     "ngpd_session_set_profiling": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "ngpd_session_get_profile": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_i32)]),
     "ngpd_session_order": (ctypes.c_int, [c_vp, c_vp, c_vp]),
@@ -255,6 +256,12 @@ class Session:
 
     def last_fixups(self) -> int:
         return load().ngpd_session_last_fixups(self._h, stream())
+
+    def knn_stats(self):
+        """(queries the 3x3x3 tier handed on, queries the 5x5x5 tier handed to the exact search) of the last kNN pass"""
+        out = (c_i32 * 2)()
+        check(load().ngpd_session_knn_stats(self._h, out, stream()), "ngpd_session_knn_stats")
+        return int(out[0]), int(out[1])
 
     def launch_count(self) -> int:
         return load().ngpd_session_launch_count(self._h)

@@ -9,19 +9,18 @@
 //               neighbours in tree order, so the lanes of one cell walk the same addresses (one L1 wavefront per
 //               distinct cell, 5-6 per warp) while no lane evaluates candidates of somebody else's block
 //               (the previous warp-union walk evaluated ~300 candidates per lane for ~80 useful ones).
-//               A candidate is turned into ONE 32-bit key: the fp32 squared distance with its 11 low mantissa bits
-//               replaced by (range slot, offset in range).  Keys below the lane's current threshold are appended
-//               to a 16-entry batch in shared memory; nothing is inserted one by one.
+//               A candidate is turned into ONE 32-bit key: 21 bits of squared distance in fixed point (units of
+//               h^2 / 65536) above 11 bits of (range slot, offset in range).  Keys below the lane's current threshold
+//               are appended to a 16-entry batch in shared memory; nothing is inserted one by one.
 //   3. select   whenever some lane's batch is nearly full, every lane sorts its batch with Batcher's odd-even merge
 //               network (63 compare-exchanges, 2 instructions each since a key carries its own id) and merges it
 //               into its sorted top-k with a bitonic half-cleaner + merge.  All lanes do the same thing at the same
 //               time: no divergence, no per-candidate insertion chains (ncu on the previous insertion kernel:
 //               10 of 32 lanes active in 34 % of its instructions).
 // Exactness is kept without fp64 in the inner loop:
-//   * keys order candidates by distance to 12 mantissa bits; a lane remembers the smallest key it ever dropped, and
-//     unless that is clearly (3e-4 relative: key truncation 2.4e-4 + fp32 evaluation error) above its k-th kept key
-//     and the k-th distance lies inside the lane's own 3x3x3 block, the query is put on a fix-up list and redone by
-//     the exact shell search;
+//   * keys order candidates by distance to 1.5e-5 h^2; a lane remembers the smallest key it ever dropped, and unless
+//     that is clearly (3 units: key truncation + fp32 evaluation error) above its k-th kept key and the k-th distance
+//     lies inside the lane's own 3x3x3 block, the query is put on a fix-up list and redone by the next tier;
 //   * the k survivors are re-evaluated in fp64 ((dx^2+dy^2)+dz^2, SciPy's order) and sorted by (distance, original
 //     index) before they are written.
 // A query answered here therefore has exactly the rows the exact kernel would give.
@@ -39,32 +38,39 @@ namespace ngpd {
 constexpr int KS_BATCH = 16;          // keys per lane between two selection rounds
 constexpr int KS_GROUP = 4;           // candidates per inner step (loads in flight); the point array is padded by KS_GROUP
 constexpr int KS_OFFBITS = 6;         // a range slot holds at most 64 points (longer ranges take several slots)
+constexpr unsigned KS_NONE = 0xffffffffu;
 constexpr unsigned FULL = 0xffffffffu;
 
+// Key of a candidate: [ squared distance in units of h^2 * 2^-16 (R = 1) | range slot | offset in the slot ].
+// The distance field is the mantissa of  y = d2 / h^2 + 32  (y in [32,64): fixed exponent, so the mantissa IS the
+// fixed-point value; every candidate of a (2R+1)^3 block has d2 < 27 h^2 < 32 h^2), which costs one FFMA and two
+// logic instructions.  Keys of different candidates are different, unsigned compare orders them by distance to
+// 1.5e-5 h^2, and min/max on them moves distance and id together.
 template <int R>
 struct KsCfg {
     static constexpr int ROWS = (2 * R + 1) * (2 * R + 1);
     static constexpr int SLOTS = 2 * ROWS;                       // a row of 2R+1 <= 8 cells crosses at most one brick boundary
     static constexpr int SLOTBITS = R == 1 ? 5 : 6;
-    static constexpr unsigned IDMASK = (1u << (SLOTBITS + KS_OFFBITS)) - 1u;
+    static constexpr int IDBITS = SLOTBITS + KS_OFFBITS;
+    static constexpr unsigned IDMASK = (1u << IDBITS) - 1u;
     static constexpr int THREADS = R == 1 ? 128 : 64;
-    static constexpr double MARGIN = R == 1 ? 3e-4 : 6e-4;       // key truncation (2^-12 / 2^-11) + fp32 evaluation error
+    static constexpr double UNIT = 1.0 / (double)(1 << (18 - (IDBITS - 9)));   // of the distance field, in h^2
 };
 
 template <int R>
 struct KsShared {
     int2 rng[KsCfg<R>::SLOTS][KsCfg<R>::THREADS];   // (first point, one past the last) of each slot
-    float batch[KS_BATCH][KsCfg<R>::THREADS];
+    unsigned batch[KS_BATCH][KsCfg<R>::THREADS];
 };
 
-__device__ __forceinline__ void ks_ce(float& a, float& b) {
-    float lo = fminf(a, b), hi = fmaxf(a, b);
+__device__ __forceinline__ void ks_ce(unsigned& a, unsigned& b) {
+    unsigned lo = min(a, b), hi = max(a, b);
     a = lo; b = hi;
 }
 
 // Batcher's odd-even merge sort, fully unrolled: every index is a compile-time constant
 template <int N>
-__device__ __forceinline__ void ks_sort(float (&a)[N]) {
+__device__ __forceinline__ void ks_sort(unsigned (&a)[N]) {
 #pragma unroll
     for (int p = 1; p < N; p *= 2)
 #pragma unroll
@@ -78,7 +84,7 @@ __device__ __forceinline__ void ks_sort(float (&a)[N]) {
 
 // ascending sort of a bitonic sequence
 template <int N>
-__device__ __forceinline__ void ks_bitonic_merge(float (&a)[N]) {
+__device__ __forceinline__ void ks_bitonic_merge(unsigned (&a)[N]) {
 #pragma unroll
     for (int k = N / 2; k >= 1; k /= 2)
 #pragma unroll
@@ -88,28 +94,34 @@ __device__ __forceinline__ void ks_bitonic_merge(float (&a)[N]) {
 
 template <int K>
 struct KsTop {
-    float key[K];     // ascending
+    unsigned key[K];  // ascending
     int id[K];        // filled by the decode step
 };
 
+template <int R>
+__device__ __forceinline__ unsigned ks_dist_field(float d2, float inv_h2) {
+    float y = fminf(fmaf(d2, inv_h2, 32.0f), 63.99999f);      // NaN and far-away candidates saturate
+    return (__float_as_uint(y) << 9) & ~KsCfg<R>::IDMASK;
+}
+
 // one selection round: the lane's batch (cnt keys in shared memory) is merged into its top-k
 template <int K, int R>
-__device__ __forceinline__ void ks_round(KsTop<K>& t, KsShared<R>& sm, int cnt, float& rej) {
+__device__ __forceinline__ void ks_round(KsTop<K>& t, KsShared<R>& sm, int cnt, unsigned& rej) {
     const int tid = threadIdx.x;
-    float b[KS_BATCH];
+    unsigned b[KS_BATCH];
 #pragma unroll
-    for (int i = 0; i < KS_BATCH; ++i) { float v = sm.batch[i][tid]; b[i] = i < cnt ? v : INFINITY; }
+    for (int i = 0; i < KS_BATCH; ++i) { unsigned v = sm.batch[i][tid]; b[i] = i < cnt ? v : KS_NONE; }
     ks_sort<KS_BATCH>(b);
     constexpr int M = K < KS_BATCH ? K : KS_BATCH;
     // top (ascending) against the batch (descending): the minima are the k smallest of both and form a bitonic sequence
 #pragma unroll
     for (int i = 0; i < M; ++i) {
-        float lo = fminf(t.key[K - 1 - i], b[i]), hi = fmaxf(t.key[K - 1 - i], b[i]);
+        unsigned lo = min(t.key[K - 1 - i], b[i]), hi = max(t.key[K - 1 - i], b[i]);
         t.key[K - 1 - i] = lo;
-        rej = fminf(rej, hi);
+        rej = min(rej, hi);
     }
     ks_bitonic_merge<K>(t.key);
-    if (K < KS_BATCH) rej = fminf(rej, b[K < KS_BATCH ? K : 0]);
+    if (K < KS_BATCH) rej = min(rej, b[K < KS_BATCH ? K : 0]);
 }
 
 // Search of the (2R+1)^3 block of cells around the lane's own cell.  Returns true when t.id[] holds the lane's final
@@ -123,6 +135,7 @@ __device__ __forceinline__ bool knn_stream(KsTop<K>& t, KsShared<R>& sm, const G
     const int cx = min(max((int)floor(rx * g.inv_h), 0), g.nx - 1);
     const int cy = min(max((int)floor(ry * g.inv_h), 0), g.ny - 1);
     const int cz = min(max((int)floor(rz * g.inv_h), 0), g.nz - 1);
+    const float inv_h2 = (float)(g.inv_h * g.inv_h);
 
     // ---- phase 1: the block's point ranges, the lane's own row first
     int nr = 0;
@@ -160,13 +173,14 @@ __device__ __forceinline__ bool knn_stream(KsTop<K>& t, KsShared<R>& sm, const G
 
     // ---- phase 2 + 3: stream the ranges four candidates at a time, select in rounds
 #pragma unroll
-    for (int a = 0; a < K; ++a) t.key[a] = INFINITY;
-    float tau = bound, rej = INFINITY;
+    for (int a = 0; a < K; ++a) t.key[a] = KS_NONE;
+    const unsigned bkey = bound < INFINITY ? (ks_dist_field<R>(bound, inv_h2) | C::IDMASK) : KS_NONE;
+    unsigned tau = bkey, rej = KS_NONE;
     const float4* pp = g.pts;
     int rem = 0, r = 0;
     unsigned idv = 0;
-    float* const b0 = &sm.batch[0][tid];
-    float* bp = b0;
+    unsigned* const b0 = &sm.batch[0][tid];
+    unsigned* bp = b0;
     if (nr > 0) { int2 q = sm.rng[0][tid]; pp = g.pts + q.x; rem = q.y - q.x; r = 1; }
     while (__any_sync(FULL, rem > 0)) {
         float4 p[KS_GROUP];
@@ -178,10 +192,11 @@ __device__ __forceinline__ bool knn_stream(KsTop<K>& t, KsShared<R>& sm, const G
             float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
             bool valid = u < rem;
             if (SELF) valid = valid && (__float_as_int(p[u].w) != self_orig);
-            float key = valid ? __uint_as_float((__float_as_uint(d2) & ~C::IDMASK) | (idv + u)) : INFINITY;
-            bool take = key < tau;
-            if (take) { *bp = key; bp += C::THREADS; }
-            rej = fminf(rej, take ? INFINITY : key);
+            const unsigned key = valid ? (ks_dist_field<R>(d2, inv_h2) | (idv + u)) : KS_NONE;
+            const bool take = key < tau;
+            *bp = key;                                                 // always stored, kept only if the pointer moves on
+            bp += take ? C::THREADS : 0;
+            rej = min(rej, take ? KS_NONE : key);
         }
         rem -= KS_GROUP;
         if (rem > 0) { pp += KS_GROUP; idv += KS_GROUP; }
@@ -190,7 +205,7 @@ __device__ __forceinline__ bool knn_stream(KsTop<K>& t, KsShared<R>& sm, const G
         if (__any_sync(FULL, bp > b0 + (KS_BATCH - KS_GROUP) * C::THREADS)) {
             ks_round<K, R>(t, sm, (int)(bp - b0) / C::THREADS, rej);
             bp = b0;
-            tau = fminf(bound, t.key[K - 1]);
+            tau = min(bkey, t.key[K - 1]);
         }
     }
     if (__any_sync(FULL, bp > b0)) ks_round<K, R>(t, sm, (int)(bp - b0) / C::THREADS, rej);
@@ -198,16 +213,14 @@ __device__ __forceinline__ bool knn_stream(KsTop<K>& t, KsShared<R>& sm, const G
     // ---- decode the survivors' ids
 #pragma unroll
     for (int a = 0; a < K; ++a) {
-        unsigned bits = __float_as_uint(t.key[a]);
-        bool real = t.key[a] < INFINITY;
+        const unsigned bits = t.key[a];
         int slot = min((int)((bits & C::IDMASK) >> KS_OFFBITS), C::SLOTS - 1);
-        t.id[a] = real ? sm.rng[slot][tid].x + (int)(bits & ((1u << KS_OFFBITS) - 1u)) : -1;
+        t.id[a] = bits != KS_NONE ? sm.rng[slot][tid].x + (int)(bits & ((1u << KS_OFFBITS) - 1u)) : -1;
     }
     if (!active || over) return false;
     // the lane saw every point of its block: final iff the list is full, its k-th distance lies inside the block, and
-    // no dropped candidate is within the key resolution of it
-    const float worst = __uint_as_float(__float_as_uint(t.key[K - 1]) & ~C::IDMASK);
-    const float rejt = __uint_as_float(__float_as_uint(rej) & ~C::IDMASK);
+    // no dropped candidate is within the key resolution (+ the fp32 evaluation error) of it
+    const unsigned worst = t.key[K - 1] >> C::IDBITS, rejv = rej >> C::IDBITS;
     double reach = DBL_MAX;
     if (cx - R > 0) reach = fmin(reach, rx - (double)(cx - R) * g.h);
     if (cx + R < g.nx - 1) reach = fmin(reach, (double)(cx + R + 1) * g.h - rx);
@@ -215,11 +228,11 @@ __device__ __forceinline__ bool knn_stream(KsTop<K>& t, KsShared<R>& sm, const G
     if (cy + R < g.ny - 1) reach = fmin(reach, (double)(cy + R + 1) * g.h - ry);
     if (cz - R > 0) reach = fmin(reach, rz - (double)(cz - R) * g.h);
     if (cz + R < g.nz - 1) reach = fmin(reach, (double)(cz + R + 1) * g.h - rz);
-    const double wmax = (double)worst * (1.0 + C::MARGIN);
+    const double wmax = (double)(worst + 3u) * C::UNIT * (g.h * g.h);
     const double rr = reach - g.h * 1e-9;
     const bool inside = (reach == DBL_MAX) ? true : (rr > 0.0 && wmax < rr * rr);
-    const bool clear = (double)rejt > wmax;
-    return t.key[K - 1] < INFINITY && inside && clear;
+    const bool clear = rejv > worst + 3u;
+    return t.key[K - 1] != KS_NONE && inside && clear;
 }
 
 // exact re-evaluation and ordering of the k kept candidates: (fp64 distance, original index).  On return t.id[] are

@@ -569,6 +569,13 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_last_fixups(n
     cudaStreamSynchronize((cudaStream_t)stream_);
     return c;
 }
+// {queries the 3x3x3 tier handed on, queries the 5x5x5 tier handed to the exact search} of the last kNN pass (synchronises)
+extern "C" __attribute__((visibility("default"))) int ngpd_session_knn_stats(ngpd_session_t* S, int32_t* out2_host, void* stream_) {
+    NGPD_REQUIRE(S && out2_host, "ngpd_session_knn_stats: NULL argument");
+    NGPD_CUDA_OK(cudaMemcpyAsync(out2_host, S->fix + 2 * S->n, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream_));
+    NGPD_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream_));
+    return 0;
+}
 
 extern "C" __attribute__((visibility("default"))) int ngpd_session_set_profiling(ngpd_session_t* S, int on) {
     NGPD_REQUIRE(S, "ngpd_session_set_profiling: NULL session");
