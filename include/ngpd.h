@@ -139,12 +139,15 @@ int ngpd_session_mean_edge_length(ngpd_session_t* s, int k, double* out_host, vo
  * get_profile returns and clears the totals (ms_out[5], launches_out[5]); it waits for the recorded events. */
 int ngpd_session_set_profiling(ngpd_session_t* s, int on);
 int ngpd_session_get_profile(ngpd_session_t* s, double* ms_out, int32_t* launches_out);
-/* kNN mode of the session: 0 = warp-lockstep fast path + exact fix-up (default), 1 = exact shell search for every
- * query.  Both give the same rows.  last_fixups = queries the last kNN pass handed to the exact search (synchronises). */
+/* kNN of the session.  The index is frozen and only the queries move, so every search also stores 2k candidates, the
+ * query position and a certified radius per row; the next pass first re-ranks those candidates (tier 0) and searches
+ * the grid only for rows that moved too far (3x3x3 streaming tier, 5x5x5 tier, exact shell search).  All tiers give
+ * bit-identical rows.  mode 0 = all tiers (default), 1 = exact shell search for every query, 2 = no re-ranking tier.
+ * last_fixups = rows the last pass handed to the exact search; knn_stats out3_host = {rows tier 0 handed to the
+ * search, rows the 3x3x3 tier handed on, rows the 5x5x5 tier handed to the exact search}.  Both synchronise. */
 int ngpd_session_set_knn_mode(ngpd_session_t* s, int mode);
 int ngpd_session_last_fixups(ngpd_session_t* s, void* stream);
-/* out2_host = {queries the 3x3x3 tier of the last kNN pass handed on, queries the 5x5x5 tier handed to the exact search} */
-int ngpd_session_knn_stats(ngpd_session_t* s, int32_t* out2_host, void* stream);
+int ngpd_session_knn_stats(ngpd_session_t* s, int32_t* out3_host, void* stream);
 /* number of kernels the last ngpd_session_step launched */
 int ngpd_session_launch_count(const ngpd_session_t* s);
 /* tree-order views for tests/benchmarks: perm (sorted -> original) */
@@ -168,7 +171,8 @@ int ngpd_session_phase_commit_normals(ngpd_session_t* s);
  * (read-only for this rank).  NULL clears the mask. */
 int ngpd_session_set_owned(ngpd_session_t* s, const uint8_t* owned_tree_order, void* stream);
 /* device views of session state in tree order: 0 positions (float4), 1 normals (float4), 2 smoothed normals
- * (float4), 3 flat-step accumulators (4 doubles), 4 centre+delta (4 floats), 5 labels (u8), 6 neighbour table */
+ * (float4), 3 flat-step accumulators (4 doubles), 4 centre+delta (4 floats), 5 labels (u8), 6 neighbour table,
+ * 7 hand-over lists of the last kNN pass (int32: n rows each of tiers 0, 1, 2, then the three counters; diagnostics) */
 void* ngpd_session_buffer(ngpd_session_t* s, int which);
 /* halo traffic: gather / scatter float4 rows of buffer `which` (0..2) listed by tree position */
 int ngpd_session_export_rows(ngpd_session_t* s, int which, const int32_t* rows, int64_t m, float* out4, void* stream);

@@ -251,17 +251,19 @@ class Session:
         check(load().ngpd_session_get_profile(self._h, ms, cnt), "ngpd_session_get_profile")
         return {name: (ms[i], cnt[i]) for i, name in enumerate(self.PROFILE_NAMES)}
 
-    def set_knn_mode(self, exact_only: bool):
-        check(load().ngpd_session_set_knn_mode(self._h, 1 if exact_only else 0), "ngpd_session_set_knn_mode")
+    def set_knn_mode(self, mode):
+        """0 / False: all tiers (default); 1 / True: exact shell search only; 2: streaming tiers without re-ranking"""
+        check(load().ngpd_session_set_knn_mode(self._h, int(mode)), "ngpd_session_set_knn_mode")
 
     def last_fixups(self) -> int:
         return load().ngpd_session_last_fixups(self._h, stream())
 
     def knn_stats(self):
-        """(queries the 3x3x3 tier handed on, queries the 5x5x5 tier handed to the exact search) of the last kNN pass"""
-        out = (c_i32 * 2)()
+        """(rows tier 0 handed to the search, rows the 3x3x3 tier handed on, rows the 5x5x5 tier handed to the exact
+        search) of the last kNN pass"""
+        out = (c_i32 * 3)()
         check(load().ngpd_session_knn_stats(self._h, out, stream()), "ngpd_session_knn_stats")
-        return int(out[0]), int(out[1])
+        return int(out[0]), int(out[1]), int(out[2])
 
     def launch_count(self) -> int:
         return load().ngpd_session_launch_count(self._h)

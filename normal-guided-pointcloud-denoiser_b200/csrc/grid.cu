@@ -406,8 +406,24 @@ using namespace ngpd;
 extern "C" __attribute__((visibility("default"))) const char* ngpd_last_error(void) { return ngpd::get_error(); }
 extern "C" __attribute__((visibility("default"))) int ngpd_version(void) { return 100; }
 
+// The library's scratch memory is stream-ordered (cudaMallocAsync).  By default the driver's pool hands freed memory
+// back to the OS at every synchronisation, so each call would pay for mapping it again; keep it cached instead.
+static void keep_scratch_pool_cached() {
+    static bool done[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
+    done[dev] = true;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t keep = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+}
+
 extern "C" __attribute__((visibility("default"))) int ngpd_grid_create(const float* pos, int64_t n, float cell_size, int k_hint, void* stream_, ngpd_grid_t** out) {
     cudaStream_t stream = (cudaStream_t)stream_;
+    keep_scratch_pool_cached();
     NGPD_REQUIRE(out != nullptr, "ngpd_grid_create: out is NULL");
     *out = nullptr;
     NGPD_REQUIRE(pos != nullptr && n > 0, "ngpd_grid_create: empty point set");

@@ -37,10 +37,10 @@ __device__ __forceinline__ void knn_fast_body(KsShared<R>& sm, const GridView& g
     float qx = 0.f, qy = 0.f, qz = 0.f;
     if (active) { qx = __ldg(query + 3 * qi); qy = __ldg(query + 3 * qi + 1); qz = __ldg(query + 3 * qi + 2); }
     KsTop<K> top;
-    bool ok = skip_self ? knn_stream<K, R, true>(top, sm, g, qx, qy, qz, active, (int)qi, INFINITY)
-                        : knn_stream<K, R, false>(top, sm, g, qx, qy, qz, active, -1, INFINITY);
+    bool ok = skip_self ? knn_stream<K, K, R, true>(top, sm, g, qx, qy, qz, active, (int)qi, INFINITY)
+                        : knn_stream<K, K, R, false>(top, sm, g, qx, qy, qz, active, -1, INFINITY);
     double ex[K];
-    ks_finalize<K>(top, g.pts, qx, qy, qz, ex);
+    ks_finalize<K, K>(top, g.pts, qx, qy, qz, ex);
     if (active && ok) {
         int32_t* row = idx_out + qi * k;
 #pragma unroll

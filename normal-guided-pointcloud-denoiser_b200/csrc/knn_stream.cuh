@@ -92,6 +92,11 @@ __device__ __forceinline__ void ks_bitonic_merge(unsigned (&a)[N]) {
             if ((i & k) == 0) ks_ce(a[i], a[i | k]);
 }
 
+// Near-ties: when the K-th and (K+1)-th candidates are closer together than the keys can tell, the first KF = K + 4
+// keys are re-evaluated exactly and the row is taken from those; only a list without spare entries (KT == K) has to
+// hand such a query on.
+__host__ __device__ constexpr int ks_kf(int K, int KT) { return KT >= K + 4 ? K + 4 : K; }
+
 template <int K>
 struct KsTop {
     unsigned key[K];  // ascending
@@ -126,9 +131,13 @@ __device__ __forceinline__ void ks_round(KsTop<K>& t, KsShared<R>& sm, int cnt, 
 
 // Search of the (2R+1)^3 block of cells around the lane's own cell.  Returns true when t.id[] holds the lane's final
 // neighbours (tree positions, still in key order); false = hand the query to the next tier.
-template <int K, int R, bool SELF>
-__device__ __forceinline__ bool knn_stream(KsTop<K>& t, KsShared<R>& sm, const GridView& g, float qx, float qy, float qz,
-                                           bool active, int self_orig, float bound) {
+// KT >= K keys are kept.  With KT > K the extra KT-K entries are spare candidates for the re-ranking tier (ks_rerank):
+// *rlim_out receives a radius (rounded down) such that EVERY tree point closer than that to the query is among the KT
+// kept ones -- the smaller of the block's reach and the distance of the nearest candidate that was not kept.
+template <int K, int KT, int R, bool SELF>
+__device__ __forceinline__ bool knn_stream(KsTop<KT>& t, KsShared<R>& sm, const GridView& g, float qx, float qy, float qz,
+                                           bool active, int self_orig, float bound, float* rlim_out = nullptr) {
+    static_assert(KT >= K, "the kept list cannot be shorter than the row");
     using C = KsCfg<R>;
     const int tid = threadIdx.x;
     const double rx = (double)qx - g.ox, ry = (double)qy - g.oy, rz = (double)qz - g.oz;
@@ -173,8 +182,9 @@ __device__ __forceinline__ bool knn_stream(KsTop<K>& t, KsShared<R>& sm, const G
 
     // ---- phase 2 + 3: stream the ranges four candidates at a time, select in rounds
 #pragma unroll
-    for (int a = 0; a < K; ++a) t.key[a] = KS_NONE;
-    const unsigned bkey = bound < INFINITY ? (ks_dist_field<R>(bound, inv_h2) | C::IDMASK) : KS_NONE;
+    for (int a = 0; a < KT; ++a) t.key[a] = KS_NONE;
+    // the temporal bound is a bound on the K-th distance: it cannot prune a longer list
+    const unsigned bkey = (KT == K && bound < INFINITY) ? (ks_dist_field<R>(bound, inv_h2) | C::IDMASK) : KS_NONE;
     unsigned tau = bkey, rej = KS_NONE;
     const float4* pp = g.pts;
     int rem = 0, r = 0;
@@ -203,24 +213,27 @@ __device__ __forceinline__ bool knn_stream(KsTop<K>& t, KsShared<R>& sm, const G
         else if (r < nr) { int2 q = sm.rng[r][tid]; pp = g.pts + q.x; rem = q.y - q.x; idv = (unsigned)r << KS_OFFBITS; ++r; }
         else { pp = g.pts; rem = 0; }                                   // done: keep the speculative loads in bounds
         if (__any_sync(FULL, bp > b0 + (KS_BATCH - KS_GROUP) * C::THREADS)) {
-            ks_round<K, R>(t, sm, (int)(bp - b0) / C::THREADS, rej);
+            ks_round<KT, R>(t, sm, (int)(bp - b0) / C::THREADS, rej);
             bp = b0;
-            tau = min(bkey, t.key[K - 1]);
+            tau = min(bkey, t.key[KT - 1]);
         }
     }
-    if (__any_sync(FULL, bp > b0)) ks_round<K, R>(t, sm, (int)(bp - b0) / C::THREADS, rej);
+    if (__any_sync(FULL, bp > b0)) ks_round<KT, R>(t, sm, (int)(bp - b0) / C::THREADS, rej);
 
     // ---- decode the survivors' ids
 #pragma unroll
-    for (int a = 0; a < K; ++a) {
+    for (int a = 0; a < KT; ++a) {
         const unsigned bits = t.key[a];
         int slot = min((int)((bits & C::IDMASK) >> KS_OFFBITS), C::SLOTS - 1);
         t.id[a] = bits != KS_NONE ? sm.rng[slot][tid].x + (int)(bits & ((1u << KS_OFFBITS) - 1u)) : -1;
     }
+    if (rlim_out) *rlim_out = 0.0f;
     if (!active || over) return false;
     // the lane saw every point of its block: final iff the list is full, its k-th distance lies inside the block, and
     // no dropped candidate is within the key resolution (+ the fp32 evaluation error) of it
-    const unsigned worst = t.key[K - 1] >> C::IDBITS, rejv = rej >> C::IDBITS;
+    const unsigned worst = t.key[K - 1] >> C::IDBITS;
+    constexpr int KF = ks_kf(K, KT);
+    const unsigned rejv = (KF < KT ? t.key[KF < KT ? KF : 0] : rej) >> C::IDBITS;   // nearest candidate that is not re-evaluated
     double reach = DBL_MAX;
     if (cx - R > 0) reach = fmin(reach, rx - (double)(cx - R) * g.h);
     if (cx + R < g.nx - 1) reach = fmin(reach, (double)(cx + R + 1) * g.h - rx);
@@ -232,14 +245,24 @@ __device__ __forceinline__ bool knn_stream(KsTop<K>& t, KsShared<R>& sm, const G
     const double rr = reach - g.h * 1e-9;
     const bool inside = (reach == DBL_MAX) ? true : (rr > 0.0 && wmax < rr * rr);
     const bool clear = rejv > worst + 3u;
+    if (rlim_out) {
+        // candidates of the block that were not kept have a key >= rej, i.e. lie at least sqrt((rej - 3) units) away;
+        // points outside the block lie at least `reach` away
+        double lim = reach == DBL_MAX ? 3.0e38 : fmax(rr, 0.0);
+        if (rej != KS_NONE) {
+            const unsigned rj = rej >> C::IDBITS;
+            lim = fmin(lim, sqrt((double)(rj > 3u ? rj - 3u : 0u) * C::UNIT) * g.h);
+        }
+        *rlim_out = __double2float_rd(lim * (1.0 - 1e-7));
+    }
     return t.key[K - 1] != KS_NONE && inside && clear;
 }
 
 // exact re-evaluation and ordering of the k kept candidates: (fp64 distance, original index).  On return t.id[] are
 // tree positions in final order and ex[] the fp64 squared distances.  (Original indices only matter between candidates
 // at exactly the same distance; they are fetched on demand.)
-template <int K>
-__device__ __forceinline__ void ks_finalize(KsTop<K>& t, const float4* __restrict__ pts, float qx, float qy, float qz, double (&ex)[K]) {
+template <int K, int KT>
+__device__ __forceinline__ void ks_finalize(KsTop<KT>& t, const float4* __restrict__ pts, float qx, float qy, float qz, double (&ex)[K]) {
     const double dqx = (double)qx, dqy = (double)qy, dqz = (double)qz;
 #pragma unroll
     for (int a = 0; a < K; ++a) {
@@ -267,6 +290,65 @@ __device__ __forceinline__ void ks_finalize(KsTop<K>& t, const float4* __restric
             }
         }
     }
+}
+
+// ---- tier 0: re-ranking ---------------------------------------------------------------------------------------------
+// The index is frozen, only the queries move.  A search (any tier) leaves behind, per query: the position it was asked
+// from (anchor), KT = 2K candidates and a radius rlim such that every tree point closer than rlim to the anchor is among
+// the candidates.  When the query has moved by delta since, a tree point that is not a candidate is at least
+// rlim - delta away from it; so if the K-th nearest CANDIDATE is closer than that, the K nearest candidates ARE the K
+// nearest tree points and no grid walk is needed: 2K gathers, two sorting networks and a merge.  Same keys, same
+// exact fp64 ordering of the survivors and same "clear of the first rejected key" rule as the streaming search, so an
+// answer given here is bit-identical to the full search's.  Returns false = ask the full search (and re-anchor).
+template <int K>
+__device__ __forceinline__ void ks_rerank_keys(const int32_t* __restrict__ crow, int first, const float4* __restrict__ pts,
+                                               float qx, float qy, float qz, float inv_h2, unsigned (&out)[K]) {
+    int j[K];
+    const int4* c4 = reinterpret_cast<const int4*>(crow + first);
+#pragma unroll
+    for (int a = 0; a < K / 4; ++a) { int4 v = __ldg(c4 + a); j[4 * a] = v.x; j[4 * a + 1] = v.y; j[4 * a + 2] = v.z; j[4 * a + 3] = v.w; }
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+        const float4 p = __ldg(pts + max(j[a], 0));
+        const float dx = p.x - qx, dy = p.y - qy, dz = p.z - qz;
+        const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        out[a] = j[a] >= 0 ? (ks_dist_field<1>(d2, inv_h2) | (unsigned)(first + a)) : KS_NONE;
+    }
+}
+
+template <int K>
+__device__ __forceinline__ bool ks_rerank(KsTop<ks_kf(K, 2 * K)>& t, const GridView& g, const int32_t* __restrict__ crow, float4 anchor,
+                                          float qx, float qy, float qz, double (&ex)[ks_kf(K, 2 * K)]) {
+    using C = KsCfg<1>;
+    constexpr int KF = ks_kf(K, 2 * K);
+    static_assert(K % 4 == 0 && 2 * K <= (1 << C::IDBITS) && KF < 2 * K, "candidate slots must fit the key's id field");
+    const float inv_h2 = (float)(g.inv_h * g.inv_h);
+    unsigned lo[K], hi[K];
+    ks_rerank_keys<K>(crow, 0, g.pts, qx, qy, qz, inv_h2, lo);
+    ks_rerank_keys<K>(crow, K, g.pts, qx, qy, qz, inv_h2, hi);
+    ks_sort<K>(lo);
+    ks_sort<K>(hi);
+#pragma unroll
+    for (int i = 0; i < K / 2; ++i) { unsigned x = hi[i]; hi[i] = hi[K - 1 - i]; hi[K - 1 - i] = x; }   // descending (register renaming)
+#pragma unroll
+    for (int i = 0; i < K; ++i) ks_ce(lo[i], hi[i]);              // ascending against descending: two bitonic halves
+    ks_bitonic_merge<K>(lo);
+    ks_bitonic_merge<K>(hi);                                        // lo, hi = the 2K keys in ascending order
+#pragma unroll
+    for (int a = 0; a < KF; ++a) {
+        const unsigned key = a < K ? lo[a < K ? a : 0] : hi[a >= K ? a - K : 0];
+        t.key[a] = key;
+        t.id[a] = key != KS_NONE ? __ldg(crow + (key & C::IDMASK)) : -1;
+    }
+    const unsigned worst = lo[K - 1], next = hi[KF - K];
+    ks_finalize<KF, KF>(t, g.pts, qx, qy, qz, ex);
+    // distance travelled since the anchor, rounded up
+    const float ax = qx - anchor.x, ay = qy - anchor.y, az = qz - anchor.z;
+    const float delta = sqrtf(fmaf(az, az, fmaf(ay, ay, ax * ax))) * 1.000001f;
+    const bool full = worst != KS_NONE;
+    const bool clear = (next >> C::IDBITS) > (worst >> C::IDBITS) + 3u;
+    const bool inside = sqrt(ex[K - 1]) * (1.0 + 1e-12) + (double)delta < (double)anchor.w;
+    return full && clear && inside;
 }
 
 // warp-aggregated append of the lanes with `flag` to a global list

@@ -28,17 +28,21 @@ struct ngpd_session {
     uint8_t* owned = nullptr; // nullable
     int32_t* idx = nullptr;
     int idx_k = 0;
-    int32_t* fix = nullptr;   // n entries + 1 counter: queries the lockstep search hands to the exact search
+    int32_t* fix = nullptr;   // hand-over lists of the kNN tiers: 3 x n rows + 3 counters (tier 0 -> 1 -> 2 -> exact)
     bool exact_only = false;
-    // temporal bound for the next search: rk = k-th squared distance of the last search (rounded up), moved = how far the
-    // point has travelled since.  By the triangle inequality its next k-th distance is at most sqrt(rk) + moved.
-    float* rk = nullptr;
-    float* moved = nullptr;
-    int bound_k = 0;          // template K the bound was recorded for (0 = none)
-    bool use_bound = true;
+    // temporal coherence (knn_stream.cuh, tier 0): candidates + anchors left by the last searches with row template cand_k
+    int32_t* cand = nullptr;  // [n * 2 * cand_k]
+    float4* anchor = nullptr; // [n]
+    int cand_k = 0;           // 0 = nothing stored
+    bool use_rerank = true;
     double* acc = nullptr;    // 4 doubles
     float* cd = nullptr;      // centre xyz, delta
     int launches = 0;
+    int knn_launches = 0;     // kernels of the last kNN pass
+    // staging for the host-buffer entry point (packed [n,3] positions, normals, labels), allocated on first use
+    float* stage_pos = nullptr;
+    float* stage_nrm = nullptr;
+    uint8_t* stage_lab = nullptr;
     // optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline numbers)
     bool profiling = false;
     std::vector<cudaEvent_t> ev;      // pairs
@@ -77,78 +81,123 @@ __global__ void __launch_bounds__(128) session_knn_kernel(GridView g, const floa
         if (a < k) row[a] = top.id[a] >= 0 ? top.id[a] : (int32_t)s;   // fewer than k tree points: pad with self
 }
 
-// tier 1 (R = 1, every row) and tier 2 (R = 2, the rows tier 1 listed) of the streaming search
-template <int K, int R>
-__device__ __forceinline__ void session_knn_body(KsShared<R>& sm, const GridView& g, const float4* __restrict__ pos, int64_t s, bool active,
-                                                 int k, int32_t* __restrict__ idx, int32_t* __restrict__ fail_list, int32_t* __restrict__ fail_count,
-                                                 const float* __restrict__ rk_in, float* __restrict__ moved, float* __restrict__ rk_out) {
-    float4 q = active ? __ldg(pos + s) : make_float4(0.f, 0.f, 0.f, 0.f);
-    float bound = INFINITY;
-    if (active && rk_in) {
-        float r = sqrtf(rk_in[s]) + moved[s];
-        bound = r * r * 1.002f;                   // > (sqrt(rk) + moved)^2 by more than the keys' resolution
+// What a search leaves behind for the re-ranking tier (knn_stream.cuh, "tier 0"): per row the position it was asked
+// from + the certified radius (anchor.w; 0 = nothing stored), and KT = 2K candidate tree positions whose first K are the row.
+struct KnnTrack {
+    int32_t* cand;      // [n * KT]
+    float4* anchor;     // [n]
+};
+
+template <int K, int KT>
+__device__ __forceinline__ void session_write_row(int64_t s, int k, const int (&id)[KT], int32_t* __restrict__ idx) {
+    if (k == K) {
+        int4* row = reinterpret_cast<int4*>(idx + s * K);
+#pragma unroll
+        for (int a = 0; a < K / 4; ++a) row[a] = make_int4(id[4 * a], id[4 * a + 1], id[4 * a + 2], id[4 * a + 3]);
+    } else {
+#pragma unroll
+        for (int a = 0; a < K; ++a)
+            if (a < k) idx[s * k + a] = id[a];
     }
-    KsTop<K> top;
-    bool ok = knn_stream<K, R, false>(top, sm, g, q.x, q.y, q.z, active, -1, bound);
-    double ex[K];
-    ks_finalize<K>(top, g.pts, q.x, q.y, q.z, ex);
+}
+
+// tier 0: every row whose stored candidates still answer the query; the others are listed for the search tiers
+template <int K>
+__global__ void __launch_bounds__(128, 4) session_knn_rerank_kernel(GridView g, const float4* __restrict__ pos, const uint8_t* __restrict__ owned,
+                                                                 int64_t n, int k, int32_t* __restrict__ idx, KnnTrack tr,
+                                                                 int32_t* __restrict__ fail_list, int32_t* __restrict__ fail_count) {
+    const int64_t s0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = s0 < n && (!owned || owned[s0]);
+    const int64_t s = active ? s0 : 0;
+    const float4 q = __ldg(pos + s), an = __ldg(tr.anchor + s);
+    constexpr int KF = ks_kf(K, 2 * K);
+    KsTop<KF> top;
+    double ex[KF];
+    bool ok = ks_rerank<K>(top, g, tr.cand + s * (2 * K), an, q.x, q.y, q.z, ex);
+    ok = ok && active && an.w > 0.0f;
+    if (ok) session_write_row<K, KF>(s, k, top.id, idx);
+    fix_append(active && !ok, (int)s, fail_list, fail_count);
+}
+
+// tiers 1 (R = 1) and 2 (R = 2) of the streaming search.  KT == K: plain search.  KT == 2K: the search also stores
+// candidates + anchor for tier 0.
+template <int K, int KT, int R>
+__device__ __forceinline__ void session_knn_body(KsShared<R>& sm, const GridView& g, const float4* __restrict__ pos, int64_t s, bool active,
+                                                 int k, int32_t* __restrict__ idx, KnnTrack tr, int32_t* __restrict__ fail_list,
+                                                 int32_t* __restrict__ fail_count) {
+    const float4 q = active ? __ldg(pos + s) : make_float4(0.f, 0.f, 0.f, 0.f);
+    KsTop<KT> top;
+    float rlim = 0.0f;
+    const bool ok = knn_stream<K, KT, R, false>(top, sm, g, q.x, q.y, q.z, active, -1, INFINITY, KT > K ? &rlim : nullptr);
+    constexpr int KF = ks_kf(K, KT);
+    double ex[KF];
+    ks_finalize<KF, KT>(top, g.pts, q.x, q.y, q.z, ex);
     if (active && ok) {
-        if (k == K) {
-            int4* row = reinterpret_cast<int4*>(idx + s * K);
+        session_write_row<K, KT>(s, k, top.id, idx);
+        if (KT > K) {
+            int4* crow = reinterpret_cast<int4*>(tr.cand + s * KT);
 #pragma unroll
-            for (int a = 0; a < K / 4; ++a) row[a] = make_int4(top.id[4 * a], top.id[4 * a + 1], top.id[4 * a + 2], top.id[4 * a + 3]);
-        } else {
-#pragma unroll
-            for (int a = 0; a < K; ++a)
-                if (a < k) idx[s * k + a] = top.id[a];
+            for (int a = 0; a < KT / 4; ++a) crow[a] = make_int4(top.id[4 * a], top.id[4 * a + 1], top.id[4 * a + 2], top.id[4 * a + 3]);
+            tr.anchor[s] = make_float4(q.x, q.y, q.z, rlim);
         }
-        if (rk_out) { rk_out[s] = __double2float_ru(ex[K - 1]); moved[s] = 0.0f; }
     }
     fix_append(active && !ok, (int)s, fail_list, fail_count);
 }
 
-template <int K>
-__global__ void __launch_bounds__(KsCfg<1>::THREADS, K <= 16 ? 5 : 1) session_knn_fast_kernel(GridView g, const float4* __restrict__ pos, const uint8_t* __restrict__ owned,
-                                                                             int64_t n, int k, int32_t* __restrict__ idx, int32_t* __restrict__ fail_list,
-                                                                             int32_t* __restrict__ fail_count, const float* __restrict__ rk_in,
-                                                                             float* __restrict__ moved, float* __restrict__ rk_out) {
+// rows = todo_list[0 .. *todo_count) when a list is given, every (owned) row otherwise
+template <int K, int KT>
+__global__ void __launch_bounds__(KsCfg<1>::THREADS, KT <= 16 ? 5 : (KT <= 32 ? 4 : 1))
+session_knn_fast_kernel(GridView g, const float4* __restrict__ pos, const uint8_t* __restrict__ owned, int64_t n, int k,
+                        int32_t* __restrict__ idx, KnnTrack tr, const int32_t* __restrict__ todo_list,
+                        const int32_t* __restrict__ todo_count, int32_t* __restrict__ fail_list, int32_t* __restrict__ fail_count) {
     __shared__ KsShared<1> sm;
-    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool active = s < n && (!owned || owned[s]);
-    session_knn_body<K, 1>(sm, g, pos, s, active, k, idx, fail_list, fail_count, rk_in, moved, rk_out);
+    const int64_t cnt = todo_list ? (int64_t)*todo_count : n;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < cnt; base += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = base + threadIdx.x;
+        bool active = i < cnt;
+        const int64_t s = active ? (todo_list ? (int64_t)todo_list[i] : i) : 0;
+        if (!todo_list) active = active && (!owned || owned[s]);
+        session_knn_body<K, KT, 1>(sm, g, pos, s, active, k, idx, tr, fail_list, fail_count);
+    }
 }
 
-template <int K>
+template <int K, int KT>
 __global__ void __launch_bounds__(KsCfg<2>::THREADS) session_knn_wide_kernel(GridView g, const float4* __restrict__ pos, int k, int32_t* __restrict__ idx,
-                                                                             const int32_t* __restrict__ todo_list, const int32_t* __restrict__ todo_count,
-                                                                             int32_t* __restrict__ fail_list, int32_t* __restrict__ fail_count,
-                                                                             const float* __restrict__ rk_in, float* __restrict__ moved,
-                                                                             float* __restrict__ rk_out) {
+                                                                             KnnTrack tr, const int32_t* __restrict__ todo_list,
+                                                                             const int32_t* __restrict__ todo_count,
+                                                                             int32_t* __restrict__ fail_list, int32_t* __restrict__ fail_count) {
     __shared__ KsShared<2> sm;
     const int cnt = *todo_count;
     for (int base = blockIdx.x * blockDim.x; base < cnt; base += gridDim.x * blockDim.x) {
         const int i = base + threadIdx.x;
         const bool active = i < cnt;
-        session_knn_body<K, 2>(sm, g, pos, active ? (int64_t)todo_list[i] : 0, active, k, idx, fail_list, fail_count, rk_in, moved, rk_out);
+        session_knn_body<K, KT, 2>(sm, g, pos, active ? (int64_t)todo_list[i] : 0, active, k, idx, tr, fail_list, fail_count);
     }
 }
 
-template <int K>
-__global__ void __launch_bounds__(128) session_knn_fix_kernel(GridView g, const float4* __restrict__ pos, int k, int32_t* __restrict__ idx,
-                                                              const int32_t* __restrict__ fix_list, const int32_t* __restrict__ fix_count,
-                                                              float* __restrict__ moved, float* __restrict__ rk_out) {
+// last tier: exact shell search (fp64 insertion lists) for what is left -- isolated points, clouds of duplicates
+template <int K, int KT>
+__global__ void __launch_bounds__(128) session_knn_fix_kernel(GridView g, const float4* __restrict__ pos, int k, int32_t* __restrict__ idx, KnnTrack tr,
+                                                              const int32_t* __restrict__ fix_list, const int32_t* __restrict__ fix_count) {
     const int cnt = *fix_count;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
-        int64_t s = fix_list[i];
-        float4 q = __ldg(pos + s);
-        TopK<K> top;
+        const int64_t s = fix_list[i];
+        const float4 q = __ldg(pos + s);
+        TopK<KT> top;
         top.init();
-        knn_search<K>(top, g, (double)q.x, (double)q.y, (double)q.z, -1);
+        knn_search<KT>(top, g, (double)q.x, (double)q.y, (double)q.z, -1);
         int32_t* row = idx + s * k;
 #pragma unroll
         for (int a = 0; a < K; ++a)
-            if (a < k) row[a] = top.id[a] >= 0 ? top.id[a] : (int32_t)s;
-        if (rk_out) { rk_out[s] = top.id[K - 1] >= 0 ? __double2float_ru(top.d[K - 1]) : INFINITY; moved[s] = 0.0f; }
+            if (a < k) row[a] = top.id[a] >= 0 ? top.id[a] : (int32_t)s;   // fewer than k tree points: pad with self
+        if (KT > K) {
+            int4* crow = reinterpret_cast<int4*>(tr.cand + s * KT);
+#pragma unroll
+            for (int a = 0; a < KT / 4; ++a) crow[a] = make_int4(top.id[4 * a], top.id[4 * a + 1], top.id[4 * a + 2], top.id[4 * a + 3]);
+            // a full list: nothing outside it is closer than its last entry; a short one holds the whole tree
+            const float rlim = top.id[KT - 1] >= 0 ? __double2float_rd(sqrt(top.d[KT - 1]) * (1.0 - 1e-7)) : 3.0e38f;
+            tr.anchor[s] = make_float4(q.x, q.y, q.z, top.id[K - 1] >= 0 ? rlim : 0.0f);
+        }
     }
 }
 
@@ -246,21 +295,16 @@ __global__ void __launch_bounds__(256) session_class_max_kernel(Quad4 pos, const
 __global__ void __launch_bounds__(128) session_update_kernel(int kind, int key, Quad4 pos, Quad4 fn, const float4* __restrict__ edge,
                                                              const uint8_t* __restrict__ label, const uint8_t* __restrict__ owned,
                                                              const int32_t* __restrict__ idx, int64_t n, int k, int ku, float alpha, float dmax,
-                                                             const float* __restrict__ cd, float4* __restrict__ out, float* __restrict__ moved) {
+                                                             const float* __restrict__ cd, float4* __restrict__ out) {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     V3 p = pos(s);
-    const V3 p0 = p;
     if (label[s] == key && (!owned || owned[s])) {
         const int32_t* row = idx + s * k;
         if (kind == NGPD_STEP_FLAT) p = flat_point(pos, fn, s, row, ku, cd[3], alpha, dmax);
         else if (kind == NGPD_STEP_EDGE) { float4 e = __ldg(edge + s); p = edge_point(pos, fn, v3(e.x, e.y, e.z), s, row, ku, alpha, dmax); }
         else if (kind == NGPD_STEP_FEATURE) p = feature_point(pos, fn, s, row, ku, alpha, dmax);
         else if (kind == NGPD_STEP_CORNER) p = corner_point(pos, fn, s, row, ku, alpha, dmax);
-        // distance travelled since the last search, rounded up (feeds the next search's bound)
-        V3 dd = p - p0;
-        float len = sqrtf(dd.x * dd.x + dd.y * dd.y + dd.z * dd.z);
-        if (len > 0.0f) moved[s] = moved[s] + len * 1.000001f + 1e-30f;
     }
     out[s] = make_float4(p.x, p.y, p.z, 0.0f);
 }
@@ -325,22 +369,68 @@ static int ensure_idx(ngpd_session* S, int k) {
     return 0;
 }
 
-// `track`: this is the step's own search (record rk / reset moved so that the next one starts from a bound)
-template <int K>
-static void run_knn_fast(ngpd_session* S, int k, int32_t* idx, cudaStream_t st, bool track) {
+struct KnnLists {
+    int32_t *list[3], *cnt[3];
+    explicit KnnLists(ngpd_session* S) {
+        for (int t = 0; t < 3; ++t) { list[t] = S->fix + (int64_t)t * S->n; cnt[t] = S->fix + 3 * S->n + t; }
+    }
+};
+
+static inline int stride_blocks(int64_t n, int threads, int per_sm) {
+    return (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(n, threads), (int64_t)num_sms() * per_sm));
+}
+
+// the search tiers over `todo` (a list written by tier 0) or over every row (todo == false)
+template <int K, int KT>
+static void run_knn_tiers(ngpd_session* S, int k, int32_t* idx, cudaStream_t st, bool todo) {
     const GridView& g = S->grid->v;
     const float4* p = S->pos[S->cur];
-    // fix = [tier-1 fail list (n) | tier-2 fail list (n) | two counters]
-    int32_t *list1 = S->fix, *list2 = S->fix + S->n, *cnt1 = S->fix + 2 * S->n, *cnt2 = cnt1 + 1;
-    cudaMemsetAsync(cnt1, 0, 2 * sizeof(int32_t), st);
-    const float* rk_in = (track && S->bound_k == K && S->use_bound) ? S->rk : nullptr;
-    float* rk_out = track ? S->rk : nullptr;
-    session_knn_fast_kernel<K><<<(unsigned)cdiv(S->n, KsCfg<1>::THREADS), KsCfg<1>::THREADS, 0, st>>>(g, p, S->owned, S->n, k, idx, list1, cnt1, rk_in, S->moved, rk_out);
-    int wide = (int)std::min<int64_t>(cdiv(S->n, KsCfg<2>::THREADS), (int64_t)num_sms() * 16);
-    session_knn_wide_kernel<K><<<wide, KsCfg<2>::THREADS, 0, st>>>(g, p, k, idx, list1, cnt1, list2, cnt2, rk_in, S->moved, rk_out);
-    int blocks = (int)std::min<int64_t>(cdiv(S->n, 128), (int64_t)num_sms() * 8);
-    session_knn_fix_kernel<K><<<blocks, 128, 0, st>>>(g, p, k, idx, list2, cnt2, S->moved, rk_out);
-    if (track) S->bound_k = K;
+    KnnLists L(S);
+    KnnTrack tr{S->cand, S->anchor};
+    if (todo)
+        session_knn_fast_kernel<K, KT><<<stride_blocks(S->n, KsCfg<1>::THREADS, 16), KsCfg<1>::THREADS, 0, st>>>(
+            g, p, S->owned, S->n, k, idx, tr, L.list[0], L.cnt[0], L.list[1], L.cnt[1]);
+    else
+        session_knn_fast_kernel<K, KT><<<(unsigned)cdiv(S->n, KsCfg<1>::THREADS), KsCfg<1>::THREADS, 0, st>>>(
+            g, p, S->owned, S->n, k, idx, tr, nullptr, nullptr, L.list[1], L.cnt[1]);
+    session_knn_wide_kernel<K, KT><<<stride_blocks(S->n, KsCfg<2>::THREADS, 16), KsCfg<2>::THREADS, 0, st>>>(g, p, k, idx, tr, L.list[1], L.cnt[1], L.list[2], L.cnt[2]);
+    session_knn_fix_kernel<K, KT><<<stride_blocks(S->n, 128, 8), 128, 0, st>>>(g, p, k, idx, tr, L.list[2], L.cnt[2]);
+}
+
+// `track`: this is the step's own search -- it may answer from, and refreshes, the stored candidates
+template <int K>
+static int run_knn_fast(ngpd_session* S, int k, int32_t* idx, cudaStream_t st, bool track) {
+    const GridView& g = S->grid->v;
+    KnnLists L(S);
+    NGPD_CUDA_OK(cudaMemsetAsync(L.cnt[0], 0, 3 * sizeof(int32_t), st));
+    constexpr bool CAN_TRACK = K <= 16;                      // 2K keys per lane must stay in registers
+    const bool rerank_ok = S->use_rerank && CAN_TRACK;
+    if (track && rerank_ok && S->cand_k != K) {
+        // first search with this row length: (re)allocate the candidate rows, no anchors yet
+        if (S->cand) cudaFree(S->cand);
+        S->cand = nullptr; S->cand_k = 0;
+        NGPD_CUDA_OK(cudaMalloc(&S->cand, (size_t)S->n * 2 * K * sizeof(int32_t)));
+        if (!S->anchor) NGPD_CUDA_OK(cudaMalloc(&S->anchor, (size_t)S->n * sizeof(float4)));
+        NGPD_CUDA_OK(cudaMemsetAsync(S->anchor, 0, (size_t)S->n * sizeof(float4), st));
+        run_knn_tiers<K, CAN_TRACK ? 2 * K : K>(S, k, idx, st, false);
+        S->cand_k = K;
+        S->knn_launches = 3;
+        return 0;
+    }
+    if constexpr (CAN_TRACK) {
+        if (rerank_ok && S->cand_k == K) {
+            // tier 0 first; what it cannot answer is searched (tracked: re-anchored, untracked: just answered)
+            session_knn_rerank_kernel<K><<<(unsigned)cdiv(S->n, 128), 128, 0, st>>>(g, S->pos[S->cur], S->owned, S->n, k, idx, KnnTrack{S->cand, S->anchor},
+                                                                                L.list[0], L.cnt[0]);
+            if (track) run_knn_tiers<K, 2 * K>(S, k, idx, st, true);
+            else run_knn_tiers<K, K>(S, k, idx, st, true);
+            S->knn_launches = 4;
+            return 0;
+        }
+    }
+    run_knn_tiers<K, K>(S, k, idx, st, false);
+    S->knn_launches = 3;
+    return 0;
 }
 
 static int run_knn(ngpd_session* S, int k, int32_t* idx, cudaStream_t st, bool track = false) {
@@ -348,16 +438,21 @@ static int run_knn(ngpd_session* S, int k, int32_t* idx, cudaStream_t st, bool t
     const GridView& g = S->grid->v;
     const float4* p = S->pos[S->cur];
     const bool fast = !S->exact_only && k > 4 && k <= 32;
+    int rc = 0;
+    S->knn_launches = 1;
     if (fast) {
-        if (k <= 8) run_knn_fast<8>(S, k, idx, st, track);
-        else if (k <= 16) run_knn_fast<16>(S, k, idx, st, track);
-        else run_knn_fast<32>(S, k, idx, st, track);
+        // a shorter row is a prefix of a longer one (same total order): reuse the stored candidates' template when it fits
+        const int kt = (S->use_rerank && S->cand_k >= k && !track) ? S->cand_k : k;
+        if (kt <= 8) rc = run_knn_fast<8>(S, k, idx, st, track);
+        else if (kt <= 16) rc = run_knn_fast<16>(S, k, idx, st, track);
+        else rc = run_knn_fast<32>(S, k, idx, st, track);
     }
     else if (k <= 4) session_knn_kernel<4><<<b, 128, 0, st>>>(g, p, S->owned, S->n, k, idx);
     else if (k <= 8) session_knn_kernel<8><<<b, 128, 0, st>>>(g, p, S->owned, S->n, k, idx);
     else if (k <= 16) session_knn_kernel<16><<<b, 128, 0, st>>>(g, p, S->owned, S->n, k, idx);
     else if (k <= 32) session_knn_kernel<32><<<b, 128, 0, st>>>(g, p, S->owned, S->n, k, idx);
     else session_knn_kernel<64><<<b, 128, 0, st>>>(g, p, S->owned, S->n, k, idx);
+    if (rc) return rc;
     NGPD_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -369,7 +464,7 @@ using namespace ngpd;
 extern "C" __attribute__((visibility("default"))) int ngpd_session_destroy(ngpd_session_t* S) {
     if (!S) return 0;
     if (S->grid) ngpd_grid_destroy(S->grid);
-    void* bufs[] = {S->pos[0], S->pos[1], S->nrm, S->fn, S->edge, S->label, S->owned, S->idx, S->acc, S->cd, S->fix, S->rk, S->moved};
+    void* bufs[] = {S->pos[0], S->pos[1], S->nrm, S->fn, S->edge, S->label, S->owned, S->idx, S->acc, S->cd, S->fix, S->cand, S->anchor, S->stage_pos, S->stage_nrm, S->stage_lab};
     for (void* b : bufs) if (b) cudaFree(b);
     delete S;
     return 0;
@@ -394,13 +489,9 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_create(const 
     if (e == cudaSuccess) e = cudaMalloc(&S->label, (size_t)n);
     if (e == cudaSuccess) e = cudaMalloc(&S->acc, 4 * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&S->cd, 4 * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc(&S->fix, (2 * (size_t)n + 2) * sizeof(int32_t));
-    if (e == cudaSuccess) e = cudaMalloc(&S->rk, (size_t)n * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc(&S->moved, (size_t)n * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&S->fix, (3 * (size_t)n + 3) * sizeof(int32_t));
     if (e != cudaSuccess) { set_error("ngpd_session_create: %s", cudaGetErrorString(e)); ngpd_session_destroy(S); return -2; }
     NGPD_CUDA_OK(cudaMemsetAsync(S->label, 0, (size_t)n, st));
-    NGPD_CUDA_OK(cudaMemsetAsync(S->moved, 0, (size_t)n * sizeof(float), st));
-    NGPD_CUDA_OK(cudaMemsetAsync(S->rk, 0, (size_t)n * sizeof(float), st));
     NGPD_CUDA_OK(cudaMemsetAsync(S->nrm, 0, b4, st));
     // current positions start as the tree positions
     session_scatter_in_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(G->pts, tree_pos, nullptr, n, S->pos[0], nullptr);
@@ -411,7 +502,7 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_create(const 
 
 extern "C" __attribute__((visibility("default"))) int ngpd_session_set_state(ngpd_session_t* S, const float* pos, const float* nrm, void* stream_) {
     NGPD_REQUIRE(S, "ngpd_session_set_state: NULL session");
-    if (pos) S->bound_k = 0;          // positions replaced from outside: the displacement record is void
+    // (positions replaced from outside keep the stored kNN candidates usable: tier 0 measures the displacement from the anchor)
     session_scatter_in_kernel<<<(unsigned)cdiv(S->n, 256), 256, 0, (cudaStream_t)stream_>>>(S->grid->pts, pos, nrm, S->n, S->pos[S->cur], S->nrm);
     NGPD_CUDA_OK(cudaGetLastError());
     return 0;
@@ -461,7 +552,7 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_phase_feature
           else if (kf == 32) session_nvt_smooth_kernel<32><<<b, 128, 0, st>>>(pos, nq, S->owned, S->idx, S->n, kf, p->x_thresh, p->tau, p->damp, S->fn);
           else if (kf == 8) session_nvt_smooth_kernel<8><<<b, 128, 0, st>>>(pos, nq, S->owned, S->idx, S->n, kf, p->x_thresh, p->tau, p->damp, S->fn);
           else session_nvt_smooth_kernel<0><<<b, 128, 0, st>>>(pos, nq, S->owned, S->idx, S->n, kf, p->x_thresh, p->tau, p->damp, S->fn); }
-        S->launches += S->exact_only ? 2 : 4;
+        S->launches += S->knn_launches + 1;
     } else {
         { ProfScope ps(S, st, 2);
           Quad4 fq{S->fn};
@@ -504,7 +595,7 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_phase_update(
     ProfScope ps(S, st, 4);
     session_update_kernel<<<(unsigned)cdiv(S->n, 128), 128, 0, st>>>(kind, key, Quad4{S->pos[S->cur]}, Quad4{S->fn}, S->edge, S->label, S->owned,
                                                                      S->idx, S->n, S->idx_k, p->k_update, p->alpha[key], p->dmax, S->cd,
-                                                                     S->pos[S->cur ^ 1], S->moved);
+                                                                     S->pos[S->cur ^ 1]);
     NGPD_CUDA_OK(cudaGetLastError());
     S->cur ^= 1;
     S->launches += 1;
@@ -554,25 +645,27 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_mean_edge_len
     return 0;
 }
 
-// knn_mode 0: lockstep fast path + exact fix-up (default); 1: exact shell search for every query
+// knn_mode 0: re-ranking tier + streaming tiers + exact fix-up (default); 1: exact shell search for every query;
+// 2: streaming tiers without the re-ranking tier (measurements, tests)
 extern "C" __attribute__((visibility("default"))) int ngpd_session_set_knn_mode(ngpd_session_t* S, int mode) {
     NGPD_REQUIRE(S, "ngpd_session_set_knn_mode: NULL session");
     S->exact_only = mode == 1;
-    S->use_bound = mode != 2;         // mode 2: fast path without the temporal bound (measurements)
+    S->use_rerank = mode == 0;
     return 0;
 }
 // number of queries the last kNN pass handed to the exact search (synchronises the stream)
 extern "C" __attribute__((visibility("default"))) int ngpd_session_last_fixups(ngpd_session_t* S, void* stream_) {
     if (!S) return -1;
     int32_t c = 0;
-    if (cudaMemcpyAsync(&c, S->fix + 2 * S->n, sizeof(c), cudaMemcpyDeviceToHost, (cudaStream_t)stream_) != cudaSuccess) return -1;
+    if (cudaMemcpyAsync(&c, S->fix + 3 * S->n + 2, sizeof(c), cudaMemcpyDeviceToHost, (cudaStream_t)stream_) != cudaSuccess) return -1;
     cudaStreamSynchronize((cudaStream_t)stream_);
     return c;
 }
-// {queries the 3x3x3 tier handed on, queries the 5x5x5 tier handed to the exact search} of the last kNN pass (synchronises)
-extern "C" __attribute__((visibility("default"))) int ngpd_session_knn_stats(ngpd_session_t* S, int32_t* out2_host, void* stream_) {
-    NGPD_REQUIRE(S && out2_host, "ngpd_session_knn_stats: NULL argument");
-    NGPD_CUDA_OK(cudaMemcpyAsync(out2_host, S->fix + 2 * S->n, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream_));
+// {rows the re-ranking tier handed to the search, rows the 3x3x3 tier handed on, rows the 5x5x5 tier handed to the exact
+// search} of the last kNN pass (synchronises)
+extern "C" __attribute__((visibility("default"))) int ngpd_session_knn_stats(ngpd_session_t* S, int32_t* out3_host, void* stream_) {
+    NGPD_REQUIRE(S && out3_host, "ngpd_session_knn_stats: NULL argument");
+    NGPD_CUDA_OK(cudaMemcpyAsync(out3_host, S->fix + 3 * S->n, 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream_));
     NGPD_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream_));
     return 0;
 }
@@ -597,7 +690,8 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_get_profile(n
     return 0;
 }
 
-// raw device views for a multi-GPU driver and for tests: which = 0 pos, 1 nrm, 2 fn, 3 acc (double*), 4 cd (float*), 5 label, 6 idx
+// raw device views for a multi-GPU driver and for tests: which = 0 pos, 1 nrm, 2 fn, 3 acc (double*), 4 cd (float*), 5 label, 6 idx,
+// 7 kNN hand-over lists (int32: n rows each of tiers 0, 1, 2, then the three counters)
 extern "C" __attribute__((visibility("default"))) void* ngpd_session_buffer(ngpd_session_t* S, int which) {
     if (!S) return nullptr;
     switch (which) {
@@ -608,6 +702,7 @@ extern "C" __attribute__((visibility("default"))) void* ngpd_session_buffer(ngpd
         case 4: return S->cd;
         case 5: return S->label;
         case 6: return S->idx;
+        case 7: return S->fix;
         default: return nullptr;
     }
 }
@@ -637,11 +732,13 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_run_host(ngpd
     cudaStream_t st = (cudaStream_t)stream_;
     NGPD_REQUIRE(S && p && pos_host && nrm_host, "ngpd_session_run_host: NULL argument");
     size_t b3 = (size_t)S->n * 3 * sizeof(float);
-    float *dpos = nullptr, *dnrm = nullptr;
-    uint8_t* dlab = nullptr;
-    NGPD_CUDA_OK(cudaMallocAsync(&dpos, b3, st));
-    NGPD_CUDA_OK(cudaMallocAsync(&dnrm, b3, st));
-    NGPD_CUDA_OK(cudaMallocAsync(&dlab, (size_t)S->n, st));
+    // device staging lives with the session: a stream-ordered allocation per call would hand its memory back to the
+    // driver at every synchronisation and pay for mapping it again (measured: 60-340 ms per call at 10 M points)
+    if (!S->stage_pos) NGPD_CUDA_OK(cudaMalloc(&S->stage_pos, b3));
+    if (!S->stage_nrm) NGPD_CUDA_OK(cudaMalloc(&S->stage_nrm, b3));
+    if (!S->stage_lab) NGPD_CUDA_OK(cudaMalloc(&S->stage_lab, (size_t)S->n));
+    float *dpos = S->stage_pos, *dnrm = S->stage_nrm;
+    uint8_t* dlab = S->stage_lab;
     NGPD_CUDA_OK(cudaMemcpyAsync(dpos, pos_host, b3, cudaMemcpyHostToDevice, st));
     NGPD_CUDA_OK(cudaMemcpyAsync(dnrm, nrm_host, b3, cudaMemcpyHostToDevice, st));
     int rc = ngpd_session_set_state(S, dpos, dnrm, stream_);
@@ -651,9 +748,6 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_run_host(ngpd
     if (pos_out_host) NGPD_CUDA_OK(cudaMemcpyAsync(pos_out_host, dpos, b3, cudaMemcpyDeviceToHost, st));
     if (nrm_out_host) NGPD_CUDA_OK(cudaMemcpyAsync(nrm_out_host, dnrm, b3, cudaMemcpyDeviceToHost, st));
     if (labels_out_host) NGPD_CUDA_OK(cudaMemcpyAsync(labels_out_host, dlab, (size_t)S->n, cudaMemcpyDeviceToHost, st));
-    NGPD_CUDA_OK(cudaFreeAsync(dpos, st));
-    NGPD_CUDA_OK(cudaFreeAsync(dnrm, st));
-    NGPD_CUDA_OK(cudaFreeAsync(dlab, st));
     NGPD_CUDA_OK(cudaStreamSynchronize(st));
     return 0;
 }

@@ -125,7 +125,7 @@ def test_knn_fast_path_equals_exact_search(ng, k):
     sess.set_state(query, torch.nn.functional.normalize(torch.randn_like(tree), dim=1))
     s1, c1 = sess.mean_edge_length_parts(k)
     fix = sess.last_fixups()
-    sess.set_knn_mode(True)
+    sess.set_knn_mode(1)
     s2, c2 = sess.mean_edge_length_parts(k)
     print(f"\nk={k}: {fix} of {n} queries ({fix / n:.3%}) went to the exact fix-up pass")
     assert c1 == c2 and abs(s1 - s2) <= 1e-9 * abs(s2)
@@ -476,14 +476,11 @@ def test_session_large_runs_and_is_deterministic(ng):
         outs.append(sess.get_state(True))
     for a, b in zip(*outs):
         assert torch.equal(a, b)                                              # no atomics in any per-point result
-    # the three kNN modes (lockstep + temporal bound, exact shell search, lockstep without the bound) give the same run
-    for mode in (True, 2):
+    # the three kNN modes (re-ranking + streaming tiers, exact shell search, streaming tiers only) give the same run
+    for mode in (1, 2):
         sess = ng._lib.Session(cloud, 16)
         sess.set_state(cloud, nrm)
-        if mode is True:
-            sess.set_knn_mode(True)
-        else:
-            ng._lib.check(ng._lib.load().ngpd_session_set_knn_mode(sess._h, 2), "mode")
+        sess.set_knn_mode(mode)
         sess.step(params); sess.step(params)
         for a, b in zip(outs[0], sess.get_state(True)):
             assert torch.equal(a, b)
@@ -491,6 +488,53 @@ def test_session_large_runs_and_is_deterministic(ng):
     assert torch.isfinite(pos).all() and torch.isfinite(fn).all()
     assert torch.allclose(fn.norm(dim=1), torch.ones(n, device="cuda"), atol=1e-4)
     assert int(lab.max()) <= 2
+
+
+def _session_table(ng, sess, k):
+    """the session's neighbour table (tree positions, tree order) as a tensor"""
+    import ctypes
+    base = ng._lib.load().ngpd_session_buffer(sess._h, 6)
+    out = torch.empty((sess.n, k), dtype=torch.int32, device="cuda")
+    ctypes.CDLL("libcudart.so").cudaMemcpy(ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(base), ctypes.c_size_t(4 * sess.n * k), 3)
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("k_f,k_u", [(16, 8), (8, 8)])
+def test_knn_rerank_tier_is_exact(ng, k_f, k_u):
+    """Temporal coherence: after the first search most rows are answered by re-ranking the stored candidates (tier 0).
+    Every iteration's neighbour table must equal the exact shell search's, also after positions were replaced from
+    outside (set_state) with some points thrown far away."""
+    n = 400_000
+    cloud = cu(surface_cloud(n, 77, noise=0.002))
+    nrm = torch.nn.functional.normalize(torch.randn(n, 3, device="cuda"), dim=1)
+    a, b = ng._lib.Session(cloud, k_f), ng._lib.Session(cloud, k_f)
+    b.set_knn_mode(1)
+    for sess in (a, b):
+        sess.set_state(cloud, nrm)
+    s, c = a.mean_edge_length_parts(6)
+    params = ng._lib.make_params(k_feature=k_f, k_update=k_u, dmax=2 * s / c)
+    answered = []
+    for it in range(5):
+        if it == 3:
+            # outside edit: everything jitters a little, 1 % of the points jump by many cells
+            pos, nr, _ = a.get_state(False)
+            g = torch.Generator(device="cuda").manual_seed(5)
+            pos = pos + 0.05 * (s / c) * torch.randn(pos.shape, device="cuda", generator=g)
+            far = torch.rand(n, device="cuda", generator=g) < 0.01
+            pos[far] += 0.2 * torch.randn((int(far.sum()), 3), device="cuda", generator=g)
+            for sess in (a, b):
+                sess.set_state(pos, nr)
+        a.step(params); b.step(params)
+        t0, t1, t2 = a.knn_stats()
+        answered.append(1.0 - t0 / n if it > 0 else 0.0)
+        assert torch.equal(_session_table(ng, a, k_f), _session_table(ng, b, k_f)), f"iteration {it}"
+        # the mean-edge-length pass (shorter rows, untracked) reuses the candidates as well
+        assert a.mean_edge_length_parts(6) == b.mean_edge_length_parts(6)
+    for x, y in zip(a.get_state(True), b.get_state(True)):
+        assert torch.equal(x, y)
+    print(f"\nk_f={k_f}: share of rows answered by the re-ranking tier per iteration: {[round(v, 4) for v in answered]}")
+    assert answered[1] > 0.5 and answered[4] > 0.5
 
 
 def test_eigh3_device_equals_host_transcription(ng):
