@@ -152,7 +152,7 @@ __device__ __forceinline__ bool knn_stream(KsTop<KT>& t, KsShared<R>& sm, const 
     if (active) {
         const int xa = max(cx - R, 0), xb = min(cx + R, g.nx - 1);
         constexpr int W = 2 * R + 1, MID = (C::ROWS - 1) / 2;
-#pragma unroll(R == 1 ? 9 : 1)
+#pragma unroll(R == 1 ? 9 : 5)
         for (int tt = 0; tt < C::ROWS; ++tt) {
             const int o = tt == 0 ? MID : (tt <= MID ? tt - 1 : tt);      // (dy 0, dz 0) first
             const int y = cy + (o % W) - R, z = cz + (o / W) - R;
@@ -300,32 +300,66 @@ __device__ __forceinline__ void ks_finalize(KsTop<KT>& t, const float4* __restri
 // nearest tree points and no grid walk is needed: 2K gathers, two sorting networks and a merge.  Same keys, same
 // exact fp64 ordering of the survivors and same "clear of the first rejected key" rule as the streaming search, so an
 // answer given here is bit-identical to the full search's.  Returns false = ask the full search (and re-anchor).
-template <int K>
-__device__ __forceinline__ void ks_rerank_keys(const int32_t* __restrict__ crow, int first, const float4* __restrict__ pts,
-                                               float qx, float qy, float qz, float inv_h2, unsigned (&out)[K]) {
-    int j[K];
-    const int4* c4 = reinterpret_cast<const int4*>(crow + first);
+// The lane's candidate row is read through `ids(slot)`: shared memory in the session kernel (KsCandTile below), which also
+// serves the slot -> id look-ups after the sort; a plain row in global memory costs one L1 tag look-up per LANE for
+// every such access (each lane's 128-byte row is a cache line of its own).
+struct KsRowGlobal {
+    const int32_t* __restrict__ row;
+    __device__ __forceinline__ int operator()(int a) const { return __ldg(row + a); }
+};
+
+// Candidate rows of the 128 consecutive queries of a block, staged through shared memory: the block's rows are one
+// contiguous piece of the candidate array, so the loads are fully coalesced 16-byte vectors (4 cache lines per warp
+// instruction instead of 32), and the transposed tile [slot][query] (+ padding chosen per row length) is free of bank
+// conflicts both when it is filled and when a lane reads its own column.
+template <int KT>
+struct KsCandTile {
+    static constexpr int THREADS = 128;
+    static constexpr int STRIDE = KT == 16 ? 130 : 129;
+    int v[KT][STRIDE];
+    __device__ __forceinline__ void fill(const int32_t* __restrict__ cand, int64_t row0, int64_t n) {
+        constexpr int CH = KT / 4;                               // 16-byte chunks per row
+        const int4* src = reinterpret_cast<const int4*>(cand + row0 * KT);
+        const int64_t avail = (n - row0) * CH;                   // chunks that exist (tail block)
 #pragma unroll
-    for (int a = 0; a < K / 4; ++a) { int4 v = __ldg(c4 + a); j[4 * a] = v.x; j[4 * a + 1] = v.y; j[4 * a + 2] = v.z; j[4 * a + 3] = v.w; }
+        for (int i = 0; i < CH; ++i) {
+            const int c = (int)threadIdx.x + THREADS * i;
+            const int4 q = c < avail ? __ldg(src + c) : make_int4(0, 0, 0, 0);
+            const int r = c / CH, a0 = (c % CH) * 4;
+            v[a0][r] = q.x; v[a0 + 1][r] = q.y; v[a0 + 2][r] = q.z; v[a0 + 3][r] = q.w;
+        }
+    }
+};
+template <int KT>
+struct KsRowShared {
+    const KsCandTile<KT>& tile;
+    int col;
+    __device__ __forceinline__ int operator()(int a) const { return tile.v[a][col]; }
+};
+
+template <int K, class Ids>
+__device__ __forceinline__ void ks_rerank_keys(const Ids& ids, int first, const float4* __restrict__ pts,
+                                               float qx, float qy, float qz, float inv_h2, unsigned (&out)[K]) {
 #pragma unroll
     for (int a = 0; a < K; ++a) {
-        const float4 p = __ldg(pts + max(j[a], 0));
+        const int j = ids(first + a);
+        const float4 p = __ldg(pts + max(j, 0));
         const float dx = p.x - qx, dy = p.y - qy, dz = p.z - qz;
         const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-        out[a] = j[a] >= 0 ? (ks_dist_field<1>(d2, inv_h2) | (unsigned)(first + a)) : KS_NONE;
+        out[a] = j >= 0 ? (ks_dist_field<1>(d2, inv_h2) | (unsigned)(first + a)) : KS_NONE;
     }
 }
 
-template <int K>
-__device__ __forceinline__ bool ks_rerank(KsTop<ks_kf(K, 2 * K)>& t, const GridView& g, const int32_t* __restrict__ crow, float4 anchor,
+template <int K, class Ids>
+__device__ __forceinline__ bool ks_rerank(KsTop<ks_kf(K, 2 * K)>& t, const GridView& g, const Ids& ids, float4 anchor,
                                           float qx, float qy, float qz, double (&ex)[ks_kf(K, 2 * K)]) {
     using C = KsCfg<1>;
     constexpr int KF = ks_kf(K, 2 * K);
     static_assert(K % 4 == 0 && 2 * K <= (1 << C::IDBITS) && KF < 2 * K, "candidate slots must fit the key's id field");
     const float inv_h2 = (float)(g.inv_h * g.inv_h);
     unsigned lo[K], hi[K];
-    ks_rerank_keys<K>(crow, 0, g.pts, qx, qy, qz, inv_h2, lo);
-    ks_rerank_keys<K>(crow, K, g.pts, qx, qy, qz, inv_h2, hi);
+    ks_rerank_keys<K>(ids, 0, g.pts, qx, qy, qz, inv_h2, lo);
+    ks_rerank_keys<K>(ids, K, g.pts, qx, qy, qz, inv_h2, hi);
     ks_sort<K>(lo);
     ks_sort<K>(hi);
 #pragma unroll
@@ -338,7 +372,7 @@ __device__ __forceinline__ bool ks_rerank(KsTop<ks_kf(K, 2 * K)>& t, const GridV
     for (int a = 0; a < KF; ++a) {
         const unsigned key = a < K ? lo[a < K ? a : 0] : hi[a >= K ? a - K : 0];
         t.key[a] = key;
-        t.id[a] = key != KS_NONE ? __ldg(crow + (key & C::IDMASK)) : -1;
+        t.id[a] = key != KS_NONE ? ids((int)(key & C::IDMASK)) : -1;
     }
     const unsigned worst = lo[K - 1], next = hi[KF - K];
     ks_finalize<KF, KF>(t, g.pts, qx, qy, qz, ex);

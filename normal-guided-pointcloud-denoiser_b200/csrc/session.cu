@@ -36,6 +36,15 @@ struct ngpd_session {
     int cand_k = 0;           // 0 = nothing stored
     bool use_rerank = true;
     double* acc = nullptr;    // 4 doubles
+    // flat_step's neighbour sums of class 0, produced by the stage-2 kernel itself when class 0 moves first with the flat
+    // strategy: one {sum x, sum y, sum z, count} per block, reduced in a fixed order (no atomics: reproducible)
+    double* part = nullptr;   // [cdiv(n,128) * 4]
+    bool sums_ready = false;  // part[] describes the current positions and labels
+    // rows of classes 1 and 2 (the minorities: creases and corners), listed by the stage-2 kernel so that their updates
+    // touch only their own rows instead of streaming the whole cloud through once more: [2 * n rows][2 counters]
+    int32_t* cls = nullptr;
+    int32_t* inv = nullptr;   // original index -> tree position (built on the first read-back)
+    bool lists_ready = false; // cls[] matches label[]
     float* cd = nullptr;      // centre xyz, delta
     int launches = 0;
     int knn_launches = 0;     // kernels of the last kNN pass
@@ -43,6 +52,8 @@ struct ngpd_session {
     float* stage_pos = nullptr;
     float* stage_nrm = nullptr;
     uint8_t* stage_lab = nullptr;
+    cudaStream_t side = nullptr;          // second stream + events of the host-buffer entry point
+    cudaEvent_t xfer[3] = {nullptr, nullptr, nullptr};
     // optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline numbers)
     bool profiling = false;
     std::vector<cudaEvent_t> ev;      // pairs
@@ -106,14 +117,19 @@ template <int K>
 __global__ void __launch_bounds__(128, 4) session_knn_rerank_kernel(GridView g, const float4* __restrict__ pos, const uint8_t* __restrict__ owned,
                                                                  int64_t n, int k, int32_t* __restrict__ idx, KnnTrack tr,
                                                                  int32_t* __restrict__ fail_list, int32_t* __restrict__ fail_count) {
-    const int64_t s0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ KsCandTile<2 * K> tile;
+    const int64_t row0 = (int64_t)blockIdx.x * blockDim.x;
+    tile.fill(tr.cand, row0, n);
+    const int64_t s0 = row0 + threadIdx.x;
     const bool active = s0 < n && (!owned || owned[s0]);
     const int64_t s = active ? s0 : 0;
     const float4 q = __ldg(pos + s), an = __ldg(tr.anchor + s);
+    __syncthreads();
     constexpr int KF = ks_kf(K, 2 * K);
     KsTop<KF> top;
     double ex[KF];
-    bool ok = ks_rerank<K>(top, g, tr.cand + s * (2 * K), an, q.x, q.y, q.z, ex);
+    // (rows that are not this rank's, or past the end, re-rank whatever their column holds -- zeros unless searched before -- and drop the result)
+    bool ok = ks_rerank<K>(top, g, KsRowShared<2 * K>{tile, (int)threadIdx.x}, an, q.x, q.y, q.z, ex);
     ok = ok && active && an.w > 0.0f;
     if (ok) session_write_row<K, KF>(s, k, top.id, idx);
     fix_append(active && !ok, (int)s, fail_list, fail_count);
@@ -234,30 +250,105 @@ __global__ void __launch_bounds__(128) session_nvt_smooth_kernel(Quad4 pos, Quad
     fn[s] = make_float4(f.x, f.y, f.z, 0.0f);
 }
 
-// stage 2: filtered NVT on the smoothed normals, label + crease direction out
+// stage 2: filtered NVT on the smoothed normals, label + crease direction out.  With part != nullptr the kernel also
+// leaves, per block, {sum x, sum y, sum z, count} over the first ku neighbours of the rows it labelled sum_key
+// (flat_step's centre, Denoiser.py:106): the positions were just gathered, so the separate pass over the class is saved.
 template <int K>
 __global__ void __launch_bounds__(128) session_nvt_classify_kernel(Quad4 pos, Quad4 fn, const uint8_t* __restrict__ owned,
                                                                    const int32_t* __restrict__ idx, int64_t n, int k, float x_thresh,
-                                                                   float scale, uint8_t* __restrict__ label, float4* __restrict__ edge) {
+                                                                   float scale, uint8_t* __restrict__ label, float4* __restrict__ edge,
+                                                                   int sum_key, int ku, double* __restrict__ part, int32_t* __restrict__ cls) {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    if (owned && !owned[s]) return;
-    NvtResult o;
-    if (K > 0) {
-        RowRegs<K> row;
-        row.load(idx + s * K);
-        nvt_point_row<K>(pos, fn, s, row, idx + s * K, K, x_thresh, o, nullptr);
-    } else {
-        nvt_point(pos, fn, s, idx + s * k, k, x_thresh, o, nullptr);
+    const bool active = s < n && (!owned || owned[s]);
+    double sx = 0, sy = 0, sz = 0, cnt = 0;
+    int lab = -1;
+    if (active) {
+        NvtResult o;
+        if (K > 0) {
+            RowRegs<K> row;
+            row.load(idx + s * K);
+            nvt_point_row<K>(pos, fn, s, row, idx + s * K, K, x_thresh, o, nullptr);
+            lab = classify(o.w, scale);
+        } else {
+            nvt_point(pos, fn, s, idx + s * k, k, x_thresh, o, nullptr);
+            lab = classify(o.w, scale);
+        }
+        if (part && lab == sum_key) {
+            // the row is read again (an L1 hit) rather than kept in registers across the eigensolver
+            // (fp32 within the row, as the reference's own mean is; fp64 from there on: conversions and fp64 adds are the slow
+            // instructions here)
+            const int32_t* row = idx + s * (K > 0 ? K : k);
+            float fx = 0.0f, fy = 0.0f, fz = 0.0f;
+            for (int a = 0; a < ku; ++a) { V3 p = pos((int64_t)__ldg(row + a)); fx += p.x; fy += p.y; fz += p.z; }
+            sx = fx; sy = fy; sz = fz;
+            cnt = ku;
+        }
+        label[s] = (uint8_t)lab;
+        edge[s] = make_float4(o.V[0], o.V[3], o.V[6], 0.0f);
     }
-    label[s] = (uint8_t)classify(o.w, scale);
-    edge[s] = make_float4(o.V[0], o.V[3], o.V[6], 0.0f);
+    if (part) {
+        __shared__ double red[4][4];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sx += __shfl_xor_sync(0xffffffffu, sx, o); sy += __shfl_xor_sync(0xffffffffu, sy, o);
+            sz += __shfl_xor_sync(0xffffffffu, sz, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        }
+        const int w = threadIdx.x >> 5;
+        if ((threadIdx.x & 31) == 0) { red[w][0] = sx; red[w][1] = sy; red[w][2] = sz; red[w][3] = cnt; }
+        __syncthreads();
+        if (threadIdx.x < 4)
+            part[(int64_t)blockIdx.x * 4 + threadIdx.x] = ((red[0][threadIdx.x] + red[1][threadIdx.x]) + red[2][threadIdx.x]) + red[3][threadIdx.x];
+    }
+    if (cls) {
+        // block-aggregated append to the two class lists: one global atomic per block and class
+        __shared__ int wcnt[2][4], base[2];
+        const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const unsigned m1 = __ballot_sync(0xffffffffu, lab == 1), m2 = __ballot_sync(0xffffffffu, lab == 2);
+        if (lane == 0) { wcnt[0][w] = __popc(m1); wcnt[1][w] = __popc(m2); }
+        __syncthreads();
+        if (threadIdx.x < 2) {
+            const int c = threadIdx.x, tot = wcnt[c][0] + wcnt[c][1] + wcnt[c][2] + wcnt[c][3];
+            base[c] = tot ? atomicAdd(cls + 2 * n + c, tot) : 0;
+        }
+        __syncthreads();
+        if (lab == 1 || lab == 2) {
+            const int c = lab - 1;
+            int off = base[c];
+            for (int v = 0; v < w; ++v) off += wcnt[c][v];
+            off += __popc((c ? m2 : m1) & ((1u << lane) - 1u));
+            cls[(int64_t)c * n + off] = (int32_t)s;
+        }
+    }
+}
+
+// fixed-order reduction of the per-block partial sums into acc (4 doubles)
+__global__ void __launch_bounds__(1024) session_partial_reduce_kernel(const double* __restrict__ part, int64_t blocks, double* __restrict__ acc) {
+    __shared__ double red[32][4];
+    double v[4] = {0, 0, 0, 0};
+    for (int64_t b = threadIdx.x; b < blocks; b += 1024) {
+        const double2* p2 = reinterpret_cast<const double2*>(part + b * 4);
+        double2 lo = p2[0], hi = p2[1];
+        v[0] += lo.x; v[1] += lo.y; v[2] += hi.x; v[3] += hi.y;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[c] += __shfl_xor_sync(0xffffffffu, v[c], o);
+    if ((threadIdx.x & 31) == 0)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) red[threadIdx.x >> 5][c] = v[c];
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double t = 0;
+        for (int w = 0; w < 32; ++w) t += red[w][threadIdx.x];
+        acc[threadIdx.x] = t;
+    }
 }
 
 // flat_step scalars over the neighbour multiset of one class (Denoiser.py:106-107)
 __global__ void __launch_bounds__(256) session_class_sum_kernel(Quad4 pos, const uint8_t* __restrict__ owned, const uint8_t* __restrict__ label,
                                                                 int key, const int32_t* __restrict__ idx, int64_t n, int k, int ku,
-                                                                double* __restrict__ acc) {
+                                                                double* __restrict__ part) {
     double sx = 0, sy = 0, sz = 0, cnt = 0;
     for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += (int64_t)gridDim.x * blockDim.x) {
         if ((owned && !owned[s]) || label[s] != key) continue;
@@ -270,7 +361,16 @@ __global__ void __launch_bounds__(256) session_class_sum_kernel(Quad4 pos, const
         sx += __shfl_xor_sync(0xffffffffu, sx, o); sy += __shfl_xor_sync(0xffffffffu, sy, o);
         sz += __shfl_xor_sync(0xffffffffu, sz, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     }
-    if ((threadIdx.x & 31) == 0 && cnt > 0) { atomicAdd(acc, sx); atomicAdd(acc + 1, sy); atomicAdd(acc + 2, sz); atomicAdd(acc + 3, cnt); }
+    // per-block partial sums, added up in a fixed order by session_partial_reduce_kernel (reproducible, no atomics)
+    __shared__ double red[8][4];
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { red[w][0] = sx; red[w][1] = sy; red[w][2] = sz; red[w][3] = cnt; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double t = 0;
+        for (int v = 0; v < 8; ++v) t += red[v][threadIdx.x];
+        part[(int64_t)blockIdx.x * 4 + threadIdx.x] = t;
+    }
 }
 __global__ void session_center_kernel(const double* __restrict__ acc, float* __restrict__ cd) {
     double c = acc[3] > 0 ? acc[3] : 1.0;
@@ -309,6 +409,30 @@ __global__ void __launch_bounds__(128) session_update_kernel(int kind, int key, 
     out[s] = make_float4(p.x, p.y, p.z, 0.0f);
 }
 
+// one minority class, in place: the listed rows move, nothing else is touched.  Two launches because a row's neighbours
+// may be rows of the same class: every new position is computed from the snapshot before any of them is stored.
+__global__ void __launch_bounds__(128) session_update_rows_kernel(int kind, Quad4 pos, Quad4 fn, const float4* __restrict__ edge,
+                                                                  const int32_t* __restrict__ list, const int32_t* __restrict__ count,
+                                                                  const int32_t* __restrict__ idx, int k, int ku, float alpha, float dmax,
+                                                                  const float* __restrict__ cd, float4* __restrict__ moved) {
+    const int cnt = *count;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+        const int64_t s = list[i];
+        const int32_t* row = idx + s * k;
+        V3 p;
+        if (kind == NGPD_STEP_FLAT) p = flat_point(pos, fn, s, row, ku, cd[3], alpha, dmax);
+        else if (kind == NGPD_STEP_EDGE) { float4 e = __ldg(edge + s); p = edge_point(pos, fn, v3(e.x, e.y, e.z), s, row, ku, alpha, dmax); }
+        else if (kind == NGPD_STEP_FEATURE) p = feature_point(pos, fn, s, row, ku, alpha, dmax);
+        else p = corner_point(pos, fn, s, row, ku, alpha, dmax);
+        moved[i] = make_float4(p.x, p.y, p.z, 0.0f);
+    }
+}
+__global__ void __launch_bounds__(256) session_apply_rows_kernel(const int32_t* __restrict__ list, const int32_t* __restrict__ count,
+                                                                 const float4* __restrict__ moved, float4* __restrict__ pos) {
+    const int cnt = *count;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) pos[list[i]] = moved[i];
+}
+
 __global__ void __launch_bounds__(256) session_scatter_in_kernel(const float4* __restrict__ tree_pts, const float* __restrict__ pos,
                                                                  const float* __restrict__ nrm, int64_t n, float4* __restrict__ pos4,
                                                                  float4* __restrict__ nrm4) {
@@ -318,19 +442,29 @@ __global__ void __launch_bounds__(256) session_scatter_in_kernel(const float4* _
     if (pos) pos4[s] = make_float4(__ldg(pos + 3 * o), __ldg(pos + 3 * o + 1), __ldg(pos + 3 * o + 2), 0.0f);
     if (nrm) nrm4[s] = make_float4(__ldg(nrm + 3 * o), __ldg(nrm + 3 * o + 1), __ldg(nrm + 3 * o + 2), 0.0f);
 }
-__global__ void __launch_bounds__(256) session_scatter_out_kernel(const float4* __restrict__ tree_pts, const float4* __restrict__ pos4,
+// state back to the caller's order.  One thread per ORIGINAL index: the packed outputs are written fully coalesced and the
+// tree-order rows are gathered through the inverse permutation (scattering 12-byte rows from tree order instead costs a
+// read-modify-write of a 32-byte sector per row: 1.23 ms against 0.3 ms at 10 M points).
+__global__ void __launch_bounds__(256) session_inverse_kernel(const float4* __restrict__ tree_pts, int64_t n, int32_t* __restrict__ inv) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) inv[__float_as_int(__ldg(&tree_pts[s].w))] = (int32_t)s;
+}
+__global__ void __launch_bounds__(256) session_scatter_out_kernel(const int32_t* __restrict__ inv, const float4* __restrict__ pos4,
                                                                   const float4* __restrict__ nrm4, const uint8_t* __restrict__ label, int64_t n,
                                                                   float* __restrict__ pos, float* __restrict__ nrm, uint8_t* __restrict__ lab) {
-    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    int64_t o = (int64_t)__float_as_int(__ldg(&tree_pts[s].w));
-    if (pos) { float4 p = pos4[s]; pos[3 * o] = p.x; pos[3 * o + 1] = p.y; pos[3 * o + 2] = p.z; }
-    if (nrm) { float4 p = nrm4[s]; nrm[3 * o] = p.x; nrm[3 * o + 1] = p.y; nrm[3 * o + 2] = p.z; }
-    if (lab) lab[o] = label[s];
+    int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n) return;
+    const int64_t s = __ldg(inv + o);
+    if (pos) { float4 p = __ldg(pos4 + s); pos[3 * o] = p.x; pos[3 * o + 1] = p.y; pos[3 * o + 2] = p.z; }
+    if (nrm) { float4 p = __ldg(nrm4 + s); nrm[3 * o] = p.x; nrm[3 * o + 1] = p.y; nrm[3 * o + 2] = p.z; }
+    if (lab) lab[o] = __ldg(label + s);
 }
 
+// per block {sum of edge lengths, edge count, 0, 0}; session_partial_reduce_kernel adds the blocks up in a fixed order, so
+// the result does not depend on scheduling (two sessions over the same rows report bit-identical sums)
 __global__ void __launch_bounds__(256) session_edge_len_kernel(Quad4 pos, const uint8_t* __restrict__ owned, const int32_t* __restrict__ idx,
-                                                               int64_t n, int k, double* __restrict__ out2) {
+                                                               int64_t n, int k, double* __restrict__ part) {
+    __shared__ double red[8][2];
     double sum = 0, cnt = 0;
     for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += (int64_t)gridDim.x * blockDim.x) {
         if (owned && !owned[s]) continue;
@@ -340,7 +474,14 @@ __global__ void __launch_bounds__(256) session_edge_len_kernel(Quad4 pos, const 
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
-    if ((threadIdx.x & 31) == 0 && cnt > 0) { atomicAdd(out2, sum); atomicAdd(out2 + 1, cnt); }
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][0] = sum; red[threadIdx.x >> 5][1] = cnt; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double t = 0;
+        if (threadIdx.x < 2)
+            for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+        part[(int64_t)blockIdx.x * 4 + threadIdx.x] = t;
+    }
 }
 
 // halo traffic: rows listed by tree position
@@ -410,6 +551,7 @@ static int run_knn_fast(ngpd_session* S, int k, int32_t* idx, cudaStream_t st, b
         if (S->cand) cudaFree(S->cand);
         S->cand = nullptr; S->cand_k = 0;
         NGPD_CUDA_OK(cudaMalloc(&S->cand, (size_t)S->n * 2 * K * sizeof(int32_t)));
+        NGPD_CUDA_OK(cudaMemsetAsync(S->cand, 0, (size_t)S->n * 2 * K * sizeof(int32_t), st));   // rows never searched (halo) stay valid ids
         if (!S->anchor) NGPD_CUDA_OK(cudaMalloc(&S->anchor, (size_t)S->n * sizeof(float4)));
         NGPD_CUDA_OK(cudaMemsetAsync(S->anchor, 0, (size_t)S->n * sizeof(float4), st));
         run_knn_tiers<K, CAN_TRACK ? 2 * K : K>(S, k, idx, st, false);
@@ -464,8 +606,9 @@ using namespace ngpd;
 extern "C" __attribute__((visibility("default"))) int ngpd_session_destroy(ngpd_session_t* S) {
     if (!S) return 0;
     if (S->grid) ngpd_grid_destroy(S->grid);
-    void* bufs[] = {S->pos[0], S->pos[1], S->nrm, S->fn, S->edge, S->label, S->owned, S->idx, S->acc, S->cd, S->fix, S->cand, S->anchor, S->stage_pos, S->stage_nrm, S->stage_lab};
+    void* bufs[] = {S->pos[0], S->pos[1], S->nrm, S->fn, S->edge, S->label, S->owned, S->idx, S->acc, S->cd, S->fix, S->cand, S->anchor, S->part, S->cls, S->inv, S->stage_pos, S->stage_nrm, S->stage_lab};
     for (void* b : bufs) if (b) cudaFree(b);
+    if (S->side) { cudaStreamDestroy(S->side); for (cudaEvent_t e : S->xfer) if (e) cudaEventDestroy(e); }
     delete S;
     return 0;
 }
@@ -502,6 +645,7 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_create(const 
 
 extern "C" __attribute__((visibility("default"))) int ngpd_session_set_state(ngpd_session_t* S, const float* pos, const float* nrm, void* stream_) {
     NGPD_REQUIRE(S, "ngpd_session_set_state: NULL session");
+    S->sums_ready = false;
     // (positions replaced from outside keep the stored kNN candidates usable: tier 0 measures the displacement from the anchor)
     session_scatter_in_kernel<<<(unsigned)cdiv(S->n, 256), 256, 0, (cudaStream_t)stream_>>>(S->grid->pts, pos, nrm, S->n, S->pos[S->cur], S->nrm);
     NGPD_CUDA_OK(cudaGetLastError());
@@ -510,7 +654,11 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_set_state(ngp
 
 extern "C" __attribute__((visibility("default"))) int ngpd_session_get_state(ngpd_session_t* S, float* pos_out, float* nrm_out, uint8_t* labels_out, void* stream_) {
     NGPD_REQUIRE(S, "ngpd_session_get_state: NULL session");
-    session_scatter_out_kernel<<<(unsigned)cdiv(S->n, 256), 256, 0, (cudaStream_t)stream_>>>(S->grid->pts, S->pos[S->cur], S->nrm, S->label, S->n,
+    if (!S->inv) {
+        NGPD_CUDA_OK(cudaMalloc(&S->inv, (size_t)S->n * sizeof(int32_t)));
+        session_inverse_kernel<<<(unsigned)cdiv(S->n, 256), 256, 0, (cudaStream_t)stream_>>>(S->grid->pts, S->n, S->inv);
+    }
+    session_scatter_out_kernel<<<(unsigned)cdiv(S->n, 256), 256, 0, (cudaStream_t)stream_>>>(S->inv, S->pos[S->cur], S->nrm, S->label, S->n,
                                                                                              pos_out, nrm_out, labels_out);
     NGPD_CUDA_OK(cudaGetLastError());
     return 0;
@@ -518,6 +666,8 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_get_state(ngp
 
 extern "C" __attribute__((visibility("default"))) int ngpd_session_set_owned(ngpd_session_t* S, const uint8_t* owned_tree_order, void* stream_) {
     NGPD_REQUIRE(S, "ngpd_session_set_owned: NULL session");
+    S->sums_ready = false;
+    S->lists_ready = false;
     if (!owned_tree_order) { if (S->owned) cudaFree(S->owned); S->owned = nullptr; return 0; }
     if (!S->owned) NGPD_CUDA_OK(cudaMalloc(&S->owned, (size_t)S->n));
     NGPD_CUDA_OK(cudaMemcpyAsync(S->owned, owned_tree_order, (size_t)S->n, cudaMemcpyDeviceToDevice, (cudaStream_t)stream_));
@@ -532,6 +682,32 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_order(const n
 extern "C" __attribute__((visibility("default"))) int ngpd_session_launch_count(const ngpd_session_t* S) { return S ? S->launches : 0; }
 
 // ---- phases (exposed one by one so that a multi-GPU driver can exchange halos in between) -----------
+// part 0 of the feature phase in its two halves (the host-buffer entry point overlaps transfers with each of them)
+static int features_knn(ngpd_session_t* S, const ngpd_step_params_t* p, cudaStream_t st) {
+    const int kf = p->k_feature;
+    int rc = ensure_idx(S, kf);
+    if (rc) return rc;
+    S->idx_k = kf;
+    { ProfScope ps(S, st, 0); rc = run_knn(S, kf, S->idx, st, true); }
+    if (rc) return rc;
+    S->launches += S->knn_launches;
+    return 0;
+}
+static int features_smooth(ngpd_session_t* S, const ngpd_step_params_t* p, cudaStream_t st) {
+    const int kf = p->k_feature;
+    unsigned b = (unsigned)cdiv(S->n, 128);
+    Quad4 pos{S->pos[S->cur]};
+    { ProfScope ps(S, st, 1);
+      Quad4 nq{S->nrm};
+      if (kf == 16) session_nvt_smooth_kernel<16><<<b, 128, 0, st>>>(pos, nq, S->owned, S->idx, S->n, kf, p->x_thresh, p->tau, p->damp, S->fn);
+      else if (kf == 32) session_nvt_smooth_kernel<32><<<b, 128, 0, st>>>(pos, nq, S->owned, S->idx, S->n, kf, p->x_thresh, p->tau, p->damp, S->fn);
+      else if (kf == 8) session_nvt_smooth_kernel<8><<<b, 128, 0, st>>>(pos, nq, S->owned, S->idx, S->n, kf, p->x_thresh, p->tau, p->damp, S->fn);
+      else session_nvt_smooth_kernel<0><<<b, 128, 0, st>>>(pos, nq, S->owned, S->idx, S->n, kf, p->x_thresh, p->tau, p->damp, S->fn); }
+    S->launches += 1;
+    NGPD_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 extern "C" __attribute__((visibility("default"))) int ngpd_session_phase_features(ngpd_session_t* S, const ngpd_step_params_t* p, int part, void* stream_) {
     // part 0: knn + NVT + smoothing (writes fn);  part 1: NVT on fn + labels + crease direction
     cudaStream_t st = (cudaStream_t)stream_;
@@ -541,25 +717,27 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_phase_feature
     unsigned b = (unsigned)cdiv(S->n, 128);
     Quad4 pos{S->pos[S->cur]};
     if (part == 0) {
-        int rc = ensure_idx(S, kf);
+        int rc = features_knn(S, p, st);
+        if (!rc) rc = features_smooth(S, p, st);
         if (rc) return rc;
-        S->idx_k = kf;
-        { ProfScope ps(S, st, 0); rc = run_knn(S, kf, S->idx, st, true); }
-        if (rc) return rc;
-        { ProfScope ps(S, st, 1);
-          Quad4 nq{S->nrm};
-          if (kf == 16) session_nvt_smooth_kernel<16><<<b, 128, 0, st>>>(pos, nq, S->owned, S->idx, S->n, kf, p->x_thresh, p->tau, p->damp, S->fn);
-          else if (kf == 32) session_nvt_smooth_kernel<32><<<b, 128, 0, st>>>(pos, nq, S->owned, S->idx, S->n, kf, p->x_thresh, p->tau, p->damp, S->fn);
-          else if (kf == 8) session_nvt_smooth_kernel<8><<<b, 128, 0, st>>>(pos, nq, S->owned, S->idx, S->n, kf, p->x_thresh, p->tau, p->damp, S->fn);
-          else session_nvt_smooth_kernel<0><<<b, 128, 0, st>>>(pos, nq, S->owned, S->idx, S->n, kf, p->x_thresh, p->tau, p->damp, S->fn); }
-        S->launches += S->knn_launches + 1;
     } else {
+        // class 0 moves first: when it uses the flat strategy its neighbour sums come out of this kernel
+        double* part = nullptr;
+        if (p->strategy[0] == NGPD_STEP_FLAT) {
+            if (!S->part) NGPD_CUDA_OK(cudaMalloc(&S->part, (size_t)b * 4 * sizeof(double)));
+            part = S->part;
+        }
+        S->sums_ready = part != nullptr;
+        if (!S->cls) NGPD_CUDA_OK(cudaMalloc(&S->cls, (2 * (size_t)S->n + 2) * sizeof(int32_t)));
+        int32_t* cls = S->cls;
+        NGPD_CUDA_OK(cudaMemsetAsync(cls + 2 * S->n, 0, 2 * sizeof(int32_t), st));
+        S->lists_ready = true;
         { ProfScope ps(S, st, 2);
           Quad4 fq{S->fn};
-          if (kf == 16) session_nvt_classify_kernel<16><<<b, 128, 0, st>>>(pos, fq, S->owned, S->idx, S->n, kf, p->x_thresh, p->scale, S->label, S->edge);
-          else if (kf == 32) session_nvt_classify_kernel<32><<<b, 128, 0, st>>>(pos, fq, S->owned, S->idx, S->n, kf, p->x_thresh, p->scale, S->label, S->edge);
-          else if (kf == 8) session_nvt_classify_kernel<8><<<b, 128, 0, st>>>(pos, fq, S->owned, S->idx, S->n, kf, p->x_thresh, p->scale, S->label, S->edge);
-          else session_nvt_classify_kernel<0><<<b, 128, 0, st>>>(pos, fq, S->owned, S->idx, S->n, kf, p->x_thresh, p->scale, S->label, S->edge); }
+          if (kf == 16) session_nvt_classify_kernel<16><<<b, 128, 0, st>>>(pos, fq, S->owned, S->idx, S->n, kf, p->x_thresh, p->scale, S->label, S->edge, 0, p->k_update, part, cls);
+          else if (kf == 32) session_nvt_classify_kernel<32><<<b, 128, 0, st>>>(pos, fq, S->owned, S->idx, S->n, kf, p->x_thresh, p->scale, S->label, S->edge, 0, p->k_update, part, cls);
+          else if (kf == 8) session_nvt_classify_kernel<8><<<b, 128, 0, st>>>(pos, fq, S->owned, S->idx, S->n, kf, p->x_thresh, p->scale, S->label, S->edge, 0, p->k_update, part, cls);
+          else session_nvt_classify_kernel<0><<<b, 128, 0, st>>>(pos, fq, S->owned, S->idx, S->n, kf, p->x_thresh, p->scale, S->label, S->edge, 0, p->k_update, part, cls); }
         S->launches += 1;
     }
     NGPD_CUDA_OK(cudaGetLastError());
@@ -574,10 +752,16 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_phase_flat_sc
     NGPD_REQUIRE(S && p, "ngpd_session_phase_flat_scalars: NULL argument");
     Quad4 pos{S->pos[S->cur]};
     ProfScope ps(S, st, 3);
-    if (part == 0) {
-        NGPD_CUDA_OK(cudaMemsetAsync(S->acc, 0, 4 * sizeof(double), st));
-        session_class_sum_kernel<<<strided(S->n, 256), 256, 0, st>>>(pos, S->owned, S->label, key, S->idx, S->n, S->idx_k, p->k_update, S->acc);
+    if (part == 0 && key == 0 && S->sums_ready) {
+        session_partial_reduce_kernel<<<1, 1024, 0, st>>>(S->part, cdiv(S->n, 128), S->acc);
         S->launches += 1;
+    } else if (part == 0) {
+        if (!S->part) NGPD_CUDA_OK(cudaMalloc(&S->part, (size_t)cdiv(S->n, 128) * 4 * sizeof(double)));
+        const unsigned blocks = strided(S->n, 256);
+        session_class_sum_kernel<<<blocks, 256, 0, st>>>(pos, S->owned, S->label, key, S->idx, S->n, S->idx_k, p->k_update, S->part);
+        session_partial_reduce_kernel<<<1, 1024, 0, st>>>(S->part, (int64_t)blocks, S->acc);
+        S->sums_ready = false;
+        S->launches += 2;
     } else {
         session_center_kernel<<<1, 1, 0, st>>>(S->acc, S->cd);
         session_class_max_kernel<<<strided(S->n, 256), 256, 0, st>>>(pos, S->owned, S->label, key, S->idx, S->n, S->idx_k, p->k_update, S->cd);
@@ -593,11 +777,23 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_phase_update(
     int kind = p->strategy[key];
     if (kind < 0) return 0;
     ProfScope ps(S, st, 4);
+    if (key > 0 && S->lists_ready) {
+        // minority class: its rows only, in place (the other position buffer is free and holds the moved rows in between)
+        const int32_t *list = S->cls + (int64_t)(key - 1) * S->n, *count = S->cls + 2 * S->n + (key - 1);
+        session_update_rows_kernel<<<stride_blocks(S->n, 128, 16), 128, 0, st>>>(kind, Quad4{S->pos[S->cur]}, Quad4{S->fn}, S->edge, list, count, S->idx,
+                                                                              S->idx_k, p->k_update, p->alpha[key], p->dmax, S->cd, S->pos[S->cur ^ 1]);
+        session_apply_rows_kernel<<<stride_blocks(S->n, 256, 8), 256, 0, st>>>(list, count, S->pos[S->cur ^ 1], S->pos[S->cur]);
+        NGPD_CUDA_OK(cudaGetLastError());
+        S->sums_ready = false;
+        S->launches += 2;
+        return 0;
+    }
     session_update_kernel<<<(unsigned)cdiv(S->n, 128), 128, 0, st>>>(kind, key, Quad4{S->pos[S->cur]}, Quad4{S->fn}, S->edge, S->label, S->owned,
                                                                      S->idx, S->n, S->idx_k, p->k_update, p->alpha[key], p->dmax, S->cd,
                                                                      S->pos[S->cur ^ 1]);
     NGPD_CUDA_OK(cudaGetLastError());
     S->cur ^= 1;
+    S->sums_ready = false;
     S->launches += 1;
     return 0;
 }
@@ -608,11 +804,9 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_phase_commit_
     return 0;
 }
 
-extern "C" __attribute__((visibility("default"))) int ngpd_session_step(ngpd_session_t* S, const ngpd_step_params_t* p, void* stream_) {
-    NGPD_REQUIRE(S && p, "ngpd_session_step: NULL argument");
-    S->launches = 0;
+// everything after the smoothed normals: labels, then the class-sequential position update, then graph.n = f_n
+static int step_tail(ngpd_session_t* S, const ngpd_step_params_t* p, void* stream_) {
     int rc;
-    if ((rc = ngpd_session_phase_features(S, p, 0, stream_))) return rc;
     if ((rc = ngpd_session_phase_features(S, p, 1, stream_))) return rc;
     for (int key = 0; key < 3; ++key) {
         if (p->strategy[key] < 0) continue;
@@ -625,22 +819,33 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_step(ngpd_ses
     return ngpd_session_phase_commit_normals(S);
 }
 
+extern "C" __attribute__((visibility("default"))) int ngpd_session_step(ngpd_session_t* S, const ngpd_step_params_t* p, void* stream_) {
+    NGPD_REQUIRE(S && p, "ngpd_session_step: NULL argument");
+    S->launches = 0;
+    int rc;
+    if ((rc = ngpd_session_phase_features(S, p, 0, stream_))) return rc;
+    return step_tail(S, p, stream_);
+}
+
 extern "C" __attribute__((visibility("default"))) int ngpd_session_mean_edge_length(ngpd_session_t* S, int k, double* out_host, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     NGPD_REQUIRE(S && out_host && k >= 1 && k <= 64, "ngpd_session_mean_edge_length: bad argument");
     int32_t* idx = nullptr;
-    double* acc = nullptr;
+    double *acc = nullptr, *part = nullptr;
+    const unsigned blocks = strided(S->n, 256);
     NGPD_CUDA_OK(cudaMallocAsync(&idx, (size_t)S->n * k * sizeof(int32_t), st));
-    NGPD_CUDA_OK(cudaMallocAsync(&acc, 2 * sizeof(double), st));
-    NGPD_CUDA_OK(cudaMemsetAsync(acc, 0, 2 * sizeof(double), st));
+    NGPD_CUDA_OK(cudaMallocAsync(&acc, 4 * sizeof(double), st));
+    NGPD_CUDA_OK(cudaMallocAsync(&part, (size_t)blocks * 4 * sizeof(double), st));
     int rc = run_knn(S, k, idx, st);
     if (rc) return rc;
-    session_edge_len_kernel<<<strided(S->n, 256), 256, 0, st>>>(Quad4{S->pos[S->cur]}, S->owned, idx, S->n, k, acc);
+    session_edge_len_kernel<<<blocks, 256, 0, st>>>(Quad4{S->pos[S->cur]}, S->owned, idx, S->n, k, part);
+    session_partial_reduce_kernel<<<1, 1024, 0, st>>>(part, (int64_t)blocks, acc);
     double h[2];
     NGPD_CUDA_OK(cudaMemcpyAsync(h, acc, sizeof(h), cudaMemcpyDeviceToHost, st));
     NGPD_CUDA_OK(cudaStreamSynchronize(st));
     NGPD_CUDA_OK(cudaFreeAsync(idx, st));
     NGPD_CUDA_OK(cudaFreeAsync(acc, st));
+    NGPD_CUDA_OK(cudaFreeAsync(part, st));
     out_host[0] = h[0]; out_host[1] = h[1];   // {sum of edge lengths, edge count}: callers divide (and all-reduce first on multi-GPU)
     return 0;
 }
@@ -719,35 +924,79 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_import_rows(n
     NGPD_REQUIRE(S && (which >= 0 && which <= 2), "ngpd_session_import_rows: bad argument");
     if (m <= 0) return 0;
     float4* dst = which == 0 ? S->pos[S->cur] : (which == 1 ? S->nrm : S->fn);
+    if (which == 0) S->sums_ready = false;
     session_import_kernel<<<(unsigned)cdiv(m, 256), 256, 0, (cudaStream_t)stream_>>>(dst, rows, m, (const float4*)in4);
     NGPD_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-// End-to-end convenience with HOST buffers (the e2e measurement path): H2D of this step's positions and normals,
-// one or more iterations, D2H of positions, normals and labels.  Synchronous.
+// End-to-end entry point with HOST buffers (the path the e2e measurement times): this step's positions and normals in,
+// `iterations` steps, positions / normals / labels out.  Synchronous.  The PCIe transfers (49 bytes per point) cost more
+// than the iteration itself, so they are taken off the critical path where the data flow allows it:
+//   in : positions first; the k-NN search needs nothing else and runs while the normals are still arriving on a second stream;
+//   out: the normals of the result are final as soon as the last smoothing pass is done, so they leave on the second stream
+//        while labels and the position updates are still being computed; positions and labels follow.
 extern "C" __attribute__((visibility("default"))) int ngpd_session_run_host(ngpd_session_t* S, const ngpd_step_params_t* p, int iterations, const float* pos_host,
                                      const float* nrm_host, float* pos_out_host, float* nrm_out_host, uint8_t* labels_out_host,
                                      void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     NGPD_REQUIRE(S && p && pos_host && nrm_host, "ngpd_session_run_host: NULL argument");
+    NGPD_REQUIRE(p->k_feature >= 1 && p->k_feature <= 64 && p->k_update >= 1 && p->k_update <= p->k_feature,
+                 "ngpd_session: need 1 <= k_update <= k_feature <= 64");
     size_t b3 = (size_t)S->n * 3 * sizeof(float);
     // device staging lives with the session: a stream-ordered allocation per call would hand its memory back to the
     // driver at every synchronisation and pay for mapping it again (measured: 60-340 ms per call at 10 M points)
     if (!S->stage_pos) NGPD_CUDA_OK(cudaMalloc(&S->stage_pos, b3));
     if (!S->stage_nrm) NGPD_CUDA_OK(cudaMalloc(&S->stage_nrm, b3));
     if (!S->stage_lab) NGPD_CUDA_OK(cudaMalloc(&S->stage_lab, (size_t)S->n));
+    if (!S->side) {
+        NGPD_CUDA_OK(cudaStreamCreateWithFlags(&S->side, cudaStreamNonBlocking));
+        for (cudaEvent_t& e : S->xfer) NGPD_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    const unsigned b = (unsigned)cdiv(S->n, 256);
+    if (!S->inv) {
+        NGPD_CUDA_OK(cudaMalloc(&S->inv, (size_t)S->n * sizeof(int32_t)));
+        session_inverse_kernel<<<b, 256, 0, st>>>(S->grid->pts, S->n, S->inv);
+    }
     float *dpos = S->stage_pos, *dnrm = S->stage_nrm;
     uint8_t* dlab = S->stage_lab;
+    S->sums_ready = false;
+    // in: positions on the caller's stream, normals behind them on the side stream
     NGPD_CUDA_OK(cudaMemcpyAsync(dpos, pos_host, b3, cudaMemcpyHostToDevice, st));
-    NGPD_CUDA_OK(cudaMemcpyAsync(dnrm, nrm_host, b3, cudaMemcpyHostToDevice, st));
-    int rc = ngpd_session_set_state(S, dpos, dnrm, stream_);
-    for (int i = 0; i < iterations && !rc; ++i) rc = ngpd_session_step(S, p, stream_);
-    if (!rc) rc = ngpd_session_get_state(S, dpos, dnrm, dlab, stream_);
-    if (rc) return rc;
+    NGPD_CUDA_OK(cudaEventRecord(S->xfer[0], st));
+    NGPD_CUDA_OK(cudaStreamWaitEvent(S->side, S->xfer[0], 0));
+    NGPD_CUDA_OK(cudaMemcpyAsync(dnrm, nrm_host, b3, cudaMemcpyHostToDevice, S->side));
+    session_scatter_in_kernel<<<b, 256, 0, S->side>>>(S->grid->pts, nullptr, dnrm, S->n, nullptr, S->nrm);
+    NGPD_CUDA_OK(cudaEventRecord(S->xfer[1], S->side));
+    session_scatter_in_kernel<<<b, 256, 0, st>>>(S->grid->pts, dpos, nullptr, S->n, S->pos[S->cur], nullptr);
+    NGPD_CUDA_OK(cudaGetLastError());
+    bool nrm_left = false;
+    int rc = 0;
+    for (int i = 0; i < iterations && !rc; ++i) {
+        S->launches = 0;
+        rc = features_knn(S, p, st);
+        if (i == 0) NGPD_CUDA_OK(cudaStreamWaitEvent(st, S->xfer[1], 0));
+        if (!rc) rc = features_smooth(S, p, st);
+        if (!rc && i == iterations - 1 && nrm_out_host) {
+            // f_n is what graph.n will be after this iteration (Processor.py:139): send it home now
+            NGPD_CUDA_OK(cudaEventRecord(S->xfer[2], st));
+            NGPD_CUDA_OK(cudaStreamWaitEvent(S->side, S->xfer[2], 0));
+            session_scatter_out_kernel<<<b, 256, 0, S->side>>>(S->inv, nullptr, S->fn, nullptr, S->n, nullptr, dnrm, nullptr);
+            NGPD_CUDA_OK(cudaMemcpyAsync(nrm_out_host, dnrm, b3, cudaMemcpyDeviceToHost, S->side));
+            nrm_left = true;
+        }
+        if (!rc) rc = step_tail(S, p, stream_);
+    }
+    if (iterations <= 0) NGPD_CUDA_OK(cudaStreamWaitEvent(st, S->xfer[1], 0));
+    if (rc) { cudaStreamSynchronize(S->side); return rc; }
+    session_scatter_out_kernel<<<b, 256, 0, st>>>(S->inv, S->pos[S->cur], nrm_left ? nullptr : S->nrm, S->label, S->n,
+                                                   pos_out_host ? dpos : nullptr, (nrm_out_host && !nrm_left) ? dnrm : nullptr,
+                                                   labels_out_host ? dlab : nullptr);
+    NGPD_CUDA_OK(cudaGetLastError());
     if (pos_out_host) NGPD_CUDA_OK(cudaMemcpyAsync(pos_out_host, dpos, b3, cudaMemcpyDeviceToHost, st));
-    if (nrm_out_host) NGPD_CUDA_OK(cudaMemcpyAsync(nrm_out_host, dnrm, b3, cudaMemcpyDeviceToHost, st));
+    if (nrm_out_host && !nrm_left) NGPD_CUDA_OK(cudaMemcpyAsync(nrm_out_host, dnrm, b3, cudaMemcpyDeviceToHost, st));
     if (labels_out_host) NGPD_CUDA_OK(cudaMemcpyAsync(labels_out_host, dlab, (size_t)S->n, cudaMemcpyDeviceToHost, st));
+    NGPD_CUDA_OK(cudaStreamSynchronize(S->side));
     NGPD_CUDA_OK(cudaStreamSynchronize(st));
     return 0;
 }

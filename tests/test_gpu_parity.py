@@ -582,3 +582,103 @@ def test_eigh3_device_equals_host_transcription(ng):
         bad = ~((w1.view(np.uint32) == w2.view(np.uint32)).all(1) & (V1.view(np.uint32) == V2.view(np.uint32)).all((1, 2)))
         print(f"\n{name}: {bad.sum()} of {n} tensors differ from the host transcription")
         assert bad.sum() == 0, name
+
+
+# ------------------------------------------------------------------------------------------------------
+# host-buffer entry points (the end-to-end path of bench.py) and the phase-by-phase driver
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("iterations", [1, 2])
+def test_run_host_equals_device_steps(ng, iterations):
+    """ngpd_session_run_host (pinned host buffers, transfers overlapped with the search and the updates on a second
+    stream) returns exactly what set_state + step + get_state give; calling it again continues from the new state."""
+    n = 300_000
+    cloud = surface_cloud(n, 33, noise=0.002)
+    nrm = torch.nn.functional.normalize(torch.randn(n, 3, generator=torch.Generator().manual_seed(3)), dim=1)
+    a, b = ng._lib.Session(cu(cloud), 16), ng._lib.Session(cu(cloud), 16)
+    a.set_state(cu(cloud), nrm.cuda())
+    s, c = a.mean_edge_length_parts(6)
+    params = ng._lib.make_params(dmax=2 * s / c)
+    pin = lambda *shape, dtype=torch.float32: torch.empty(shape, dtype=dtype).pin_memory()
+    pos_h, nrm_h, pos_o, nrm_o, lab_o = pin(n, 3), pin(n, 3), pin(n, 3), pin(n, 3), pin(n, dtype=torch.uint8)
+    pos_h.copy_(torch.from_numpy(cloud)); nrm_h.copy_(nrm)
+    for call in range(2):
+        for _ in range(iterations):
+            a.step(params)
+        want = [t.cpu() for t in a.get_state(True)]
+        b.run_host(params, iterations, pos_h, nrm_h, pos_o, nrm_o, lab_o)
+        for w, g, name in zip(want, (pos_o, nrm_o, lab_o), ("positions", "normals", "labels")):
+            assert torch.equal(w, g), f"call {call}: {name}"
+        pos_h.copy_(pos_o); nrm_h.copy_(nrm_o)
+    # outputs are optional
+    b.run_host(params, 1, pos_h, nrm_h, pos_o, None, None)
+    a.step(params)
+    assert torch.equal(a.get_state(False)[0].cpu(), pos_o)
+
+
+def test_denoise_host_one_shot(ng):
+    import ctypes
+    n = 50_000
+    cloud = surface_cloud(n, 34, noise=0.003)
+    nrm = torch.nn.functional.normalize(torch.randn(n, 3, generator=torch.Generator().manual_seed(4)), dim=1).numpy()
+    sess = ng._lib.Session(cu(cloud), 16)
+    sess.set_state(cu(cloud), cu(nrm))
+    s, c = sess.mean_edge_length_parts(6)
+    params = ng._lib.make_params(dmax=2 * s / c)
+    sess.step(params); sess.step(params)
+    want = [t.cpu().numpy() for t in sess.get_state(True)]
+    pos_o, nrm_o, lab_o = np.empty_like(cloud), np.empty_like(nrm), np.empty(n, np.uint8)
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    rc = ng._lib.load().ngpd_denoise_host(vp(cloud), vp(cloud), vp(nrm), n, ctypes.byref(params), 2, vp(pos_o), vp(nrm_o), vp(lab_o))
+    assert rc == 0, ng._lib.load().ngpd_last_error()
+    for w, g in zip(want, (pos_o, nrm_o, lab_o)):
+        assert np.array_equal(w, g)
+
+
+def test_phase_driver_equals_fused_step(ng):
+    """The phase entry points a multi-GPU driver calls one by one (with the flat-step scalars recomputed by their own
+    kernels after an outside edit of the positions) give the same iteration as ngpd_session_step, whose stage-2 kernel
+    produces the class-0 sums and the minority-class row lists itself."""
+    import ctypes
+    n = 200_000
+    cloud = cu(surface_cloud(n, 35, noise=0.002))
+    nrm = torch.nn.functional.normalize(torch.randn(n, 3, device="cuda"), dim=1)
+    lib = ng._lib.load()
+    outs = []
+    for mode in range(3):
+        sess = ng._lib.Session(cloud, 16)
+        sess.set_state(cloud, nrm)
+        s, c = sess.mean_edge_length_parts(6)
+        for strategy in ((ng._lib.STEP_FLAT, ng._lib.STEP_EDGE, ng._lib.STEP_FEATURE), (ng._lib.STEP_FEATURE, ng._lib.STEP_FLAT, ng._lib.STEP_CORNER)):
+            params = ng._lib.make_params(dmax=2 * s / c, strategy=strategy)
+            ref = ctypes.byref(params)
+            if mode == 0:
+                sess.step(params)
+                continue
+            st = ng._lib.stream
+            assert lib.ngpd_session_phase_features(sess._h, ref, 0, st()) == 0
+            assert lib.ngpd_session_phase_features(sess._h, ref, 1, st()) == 0
+            if mode == 2:
+                # a no-op "halo import" of positions: drops the fused sums, the stand-alone reduction must give the same centre
+                rows = torch.arange(4, dtype=torch.int32, device="cuda")
+                buf = torch.empty((4, 4), device="cuda")
+                assert lib.ngpd_session_export_rows(sess._h, 0, rows.data_ptr(), 4, buf.data_ptr(), st()) == 0
+                assert lib.ngpd_session_import_rows(sess._h, 0, rows.data_ptr(), 4, buf.data_ptr(), st()) == 0
+            for key in range(3):
+                if params.strategy[key] == ng._lib.STEP_FLAT:
+                    assert lib.ngpd_session_phase_flat_scalars(sess._h, ref, key, 0, st()) == 0
+                    assert lib.ngpd_session_phase_flat_scalars(sess._h, ref, key, 1, st()) == 0
+                assert lib.ngpd_session_phase_update(sess._h, ref, key, st()) == 0
+            assert lib.ngpd_session_phase_commit_normals(sess._h) == 0
+            if mode == 2:
+                break                                                         # one iteration is enough for the comparison below
+        outs.append(sess.get_state(True))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+    # mode 2 sums the class in a different order (atomics instead of the fixed per-block order): the centre may differ in
+    # the last bit, the positions by a few ulp.  Compared after the first iteration (labels are decided before anything moves).
+    sess = ng._lib.Session(cloud, 16)
+    sess.set_state(cloud, nrm)
+    sess.step(ng._lib.make_params(dmax=2 * s / c))
+    one = sess.get_state(True)
+    assert torch.equal(one[2], outs[2][2])
+    assert (one[0] - outs[2][0]).abs().max().item() <= 1e-6 * one[0].abs().max().item()
