@@ -32,6 +32,7 @@
 // went to the exact search: that kernel took half as long as the fast kernel for 2.4 % of the queries.
 #pragma once
 #include "knn.cuh"
+#include "sortnet.cuh"
 
 namespace ngpd {
 
@@ -62,35 +63,6 @@ struct KsShared {
     int2 rng[KsCfg<R>::SLOTS][KsCfg<R>::THREADS];   // (first point, one past the last) of each slot
     unsigned batch[KS_BATCH][KsCfg<R>::THREADS];
 };
-
-__device__ __forceinline__ void ks_ce(unsigned& a, unsigned& b) {
-    unsigned lo = min(a, b), hi = max(a, b);
-    a = lo; b = hi;
-}
-
-// Batcher's odd-even merge sort, fully unrolled: every index is a compile-time constant
-template <int N>
-__device__ __forceinline__ void ks_sort(unsigned (&a)[N]) {
-#pragma unroll
-    for (int p = 1; p < N; p *= 2)
-#pragma unroll
-        for (int k = p; k >= 1; k /= 2)
-#pragma unroll
-            for (int j = k % p; j <= N - 1 - k; j += 2 * k)
-#pragma unroll
-                for (int i = 0; i < k; ++i)
-                    if (i + j + k < N && (i + j) / (2 * p) == (i + j + k) / (2 * p)) ks_ce(a[i + j], a[i + j + k]);
-}
-
-// ascending sort of a bitonic sequence
-template <int N>
-__device__ __forceinline__ void ks_bitonic_merge(unsigned (&a)[N]) {
-#pragma unroll
-    for (int k = N / 2; k >= 1; k /= 2)
-#pragma unroll
-        for (int i = 0; i < N; ++i)
-            if ((i & k) == 0) ks_ce(a[i], a[i | k]);
-}
 
 // Near-ties: when the K-th and (K+1)-th candidates are closer together than the keys can tell, the first KF = K + 4
 // keys are re-evaluated exactly and the row is taken from those; only a list without spare entries (KT == K) has to

@@ -8,6 +8,7 @@
 // one after the other, each from a snapshot that already contains the earlier classes' moves.
 // `owned` (optional) marks the rows this rank computes; the remaining rows are halo copies of points owned by
 // another GPU, refreshed between phases by ngpd_session_{export,import}_rows.
+#include <cstdlib>
 #include <vector>
 #include <algorithm>
 #include "knn_stream.cuh"
@@ -39,6 +40,7 @@ struct ngpd_session {
     // flat_step's neighbour sums of class 0, produced by the stage-2 kernel itself when class 0 moves first with the flat
     // strategy: one {sum x, sum y, sum z, count} per block, reduced in a fixed order (no atomics: reproducible)
     double* part = nullptr;   // [cdiv(n,128) * 4]
+    double* red2 = nullptr;   // scratch of the fixed-order reduction (slice sums + ticket counter)
     bool sums_ready = false;  // part[] describes the current positions and labels
     // rows of classes 1 and 2 (the minorities: creases and corners), listed by the stage-2 kernel so that their updates
     // touch only their own rows instead of streaming the whole cloud through once more: [2 * n rows][2 counters]
@@ -52,6 +54,14 @@ struct ngpd_session {
     float* stage_pos = nullptr;
     float* stage_nrm = nullptr;
     uint8_t* stage_lab = nullptr;
+    // The last two search tiers (5x5x5 cells, exact shell search) answer ~0.1 % of the rows but take 0.2 ms of pure
+    // latency (a handful of warps walking long candidate lists).  In a step they run on their own stream while the first
+    // tensor pass already works on every other row; `late` marks the rows it has to leave for a small second launch.
+    cudaStream_t tail = nullptr;
+    cudaEvent_t tail_ev[2] = {nullptr, nullptr};
+    uint8_t* late = nullptr;              // [n], all zero between steps
+    bool overlap_tail = false;            // set by the step's search only
+    bool tail_pending = false;            // tiers 2-3 of the current search are still running on `tail`
     cudaStream_t side = nullptr;          // second stream + events of the host-buffer entry point
     cudaEvent_t xfer[3] = {nullptr, nullptr, nullptr};
     // optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline numbers)
@@ -140,7 +150,7 @@ __global__ void __launch_bounds__(128, 4) session_knn_rerank_kernel(GridView g, 
 template <int K, int KT, int R>
 __device__ __forceinline__ void session_knn_body(KsShared<R>& sm, const GridView& g, const float4* __restrict__ pos, int64_t s, bool active,
                                                  int k, int32_t* __restrict__ idx, KnnTrack tr, int32_t* __restrict__ fail_list,
-                                                 int32_t* __restrict__ fail_count) {
+                                                 int32_t* __restrict__ fail_count, uint8_t* __restrict__ late = nullptr) {
     const float4 q = active ? __ldg(pos + s) : make_float4(0.f, 0.f, 0.f, 0.f);
     KsTop<KT> top;
     float rlim = 0.0f;
@@ -158,6 +168,7 @@ __device__ __forceinline__ void session_knn_body(KsShared<R>& sm, const GridView
         }
     }
     fix_append(active && !ok, (int)s, fail_list, fail_count);
+    if (late && active && !ok) late[s] = 1;     // answered later, on the side stream: the first tensor pass skips the row
 }
 
 // rows = todo_list[0 .. *todo_count) when a list is given, every (owned) row otherwise
@@ -165,7 +176,8 @@ template <int K, int KT>
 __global__ void __launch_bounds__(KsCfg<1>::THREADS, KT <= 16 ? 5 : (KT <= 32 ? 4 : 1))
 session_knn_fast_kernel(GridView g, const float4* __restrict__ pos, const uint8_t* __restrict__ owned, int64_t n, int k,
                         int32_t* __restrict__ idx, KnnTrack tr, const int32_t* __restrict__ todo_list,
-                        const int32_t* __restrict__ todo_count, int32_t* __restrict__ fail_list, int32_t* __restrict__ fail_count) {
+                        const int32_t* __restrict__ todo_count, int32_t* __restrict__ fail_list, int32_t* __restrict__ fail_count,
+                        uint8_t* __restrict__ late) {
     __shared__ KsShared<1> sm;
     const int64_t cnt = todo_list ? (int64_t)*todo_count : n;
     for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < cnt; base += (int64_t)gridDim.x * blockDim.x) {
@@ -173,7 +185,7 @@ session_knn_fast_kernel(GridView g, const float4* __restrict__ pos, const uint8_
         bool active = i < cnt;
         const int64_t s = active ? (todo_list ? (int64_t)todo_list[i] : i) : 0;
         if (!todo_list) active = active && (!owned || owned[s]);
-        session_knn_body<K, KT, 1>(sm, g, pos, s, active, k, idx, tr, fail_list, fail_count);
+        session_knn_body<K, KT, 1>(sm, g, pos, s, active, k, idx, tr, fail_list, fail_count, late);
     }
 }
 
@@ -232,12 +244,8 @@ struct RowRegs {
 
 // stage 1: filtered NVT on the current normals, smoothed normal out
 template <int K>
-__global__ void __launch_bounds__(128) session_nvt_smooth_kernel(Quad4 pos, Quad4 nrm, const uint8_t* __restrict__ owned,
-                                                                 const int32_t* __restrict__ idx, int64_t n, int k, float x_thresh,
-                                                                 float tau, float damp, float4* __restrict__ fn) {
-    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    if (owned && !owned[s]) return;
+__device__ __forceinline__ void session_nvt_smooth_row(const Quad4& pos, const Quad4& nrm, const int32_t* __restrict__ idx, int64_t s, int k,
+                                                       float x_thresh, float tau, float damp, float4* __restrict__ fn) {
     NvtResult o;
     if (K > 0) {
         RowRegs<K> row;
@@ -249,52 +257,69 @@ __global__ void __launch_bounds__(128) session_nvt_smooth_kernel(Quad4 pos, Quad
     V3 f = smooth_normal(o.w, o.V, nrm(s), tau, damp);
     fn[s] = make_float4(f.x, f.y, f.z, 0.0f);
 }
+// every (owned) row; rows marked in `late` (nullable) are still being searched on the side stream and are left out
+template <int K>
+__global__ void __launch_bounds__(128) session_nvt_smooth_kernel(Quad4 pos, Quad4 nrm, const uint8_t* __restrict__ owned,
+                                                                 const uint8_t* __restrict__ late, const int32_t* __restrict__ idx, int64_t n, int k,
+                                                                 float x_thresh, float tau, float damp, float4* __restrict__ fn) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    if (owned && !owned[s]) return;
+    if (late && late[s]) return;
+    session_nvt_smooth_row<K>(pos, nrm, idx, s, k, x_thresh, tau, damp, fn);
+}
+// the rows left out above, once their search is done; clears their marks
+template <int K>
+__global__ void __launch_bounds__(128) session_nvt_smooth_late_kernel(Quad4 pos, Quad4 nrm, const int32_t* __restrict__ list,
+                                                                      const int32_t* __restrict__ count, uint8_t* __restrict__ late,
+                                                                      const int32_t* __restrict__ idx, int k, float x_thresh, float tau, float damp,
+                                                                      float4* __restrict__ fn) {
+    const int cnt = *count;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+        const int64_t s = list[i];
+        session_nvt_smooth_row<K>(pos, nrm, idx, s, k, x_thresh, tau, damp, fn);
+        late[s] = 0;
+    }
+}
 
 // stage 2: filtered NVT on the smoothed normals, label + crease direction out.  With part != nullptr the kernel also
 // leaves, per block, {sum x, sum y, sum z, count} over the first ku neighbours of the rows it labelled sum_key
 // (flat_step's centre, Denoiser.py:106): the positions were just gathered, so the separate pass over the class is saved.
 template <int K>
-__global__ void __launch_bounds__(128) session_nvt_classify_kernel(Quad4 pos, Quad4 fn, const uint8_t* __restrict__ owned,
+__global__ void __launch_bounds__(128, K == 16 ? 9 : 1) session_nvt_classify_kernel(Quad4 pos, Quad4 fn, const uint8_t* __restrict__ owned,
                                                                    const int32_t* __restrict__ idx, int64_t n, int k, float x_thresh,
                                                                    float scale, uint8_t* __restrict__ label, float4* __restrict__ edge,
                                                                    int sum_key, int ku, double* __restrict__ part, int32_t* __restrict__ cls) {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = s < n && (!owned || owned[s]);
-    double sx = 0, sy = 0, sz = 0, cnt = 0;
+    float fx = 0.0f, fy = 0.0f, fz = 0.0f;
     int lab = -1;
     if (active) {
         NvtResult o;
+        // the sum of the first ku neighbour positions (flat_step's centre) is accumulated inside the vote loop, where the
+        // positions are in registers anyway: fp32 within the row and the warp (the reference's own mean is fp32), fp64 above
+        V3 ps = v3(0.0f, 0.0f, 0.0f);
         if (K > 0) {
             RowRegs<K> row;
             row.load(idx + s * K);
-            nvt_point_row<K>(pos, fn, s, row, idx + s * K, K, x_thresh, o, nullptr);
-            lab = classify(o.w, scale);
+            nvt_point_row<K>(pos, fn, s, row, idx + s * K, K, x_thresh, o, nullptr, part ? &ps : nullptr, ku);
         } else {
-            nvt_point(pos, fn, s, idx + s * k, k, x_thresh, o, nullptr);
-            lab = classify(o.w, scale);
+            nvt_point_row<0>(pos, fn, s, RowPtr<int32_t>{idx + s * k}, idx + s * k, k, x_thresh, o, nullptr, part ? &ps : nullptr, ku);
         }
-        if (part && lab == sum_key) {
-            // the row is read again (an L1 hit) rather than kept in registers across the eigensolver
-            // (fp32 within the row, as the reference's own mean is; fp64 from there on: conversions and fp64 adds are the slow
-            // instructions here)
-            const int32_t* row = idx + s * (K > 0 ? K : k);
-            float fx = 0.0f, fy = 0.0f, fz = 0.0f;
-            for (int a = 0; a < ku; ++a) { V3 p = pos((int64_t)__ldg(row + a)); fx += p.x; fy += p.y; fz += p.z; }
-            sx = fx; sy = fy; sz = fz;
-            cnt = ku;
-        }
+        lab = classify(o.w, scale);
+        if (lab == sum_key) { fx = ps.x; fy = ps.y; fz = ps.z; }
         label[s] = (uint8_t)lab;
         edge[s] = make_float4(o.V[0], o.V[3], o.V[6], 0.0f);
     }
     if (part) {
         __shared__ double red[4][4];
+        const unsigned members = __ballot_sync(0xffffffffu, lab == sum_key);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            sx += __shfl_xor_sync(0xffffffffu, sx, o); sy += __shfl_xor_sync(0xffffffffu, sy, o);
-            sz += __shfl_xor_sync(0xffffffffu, sz, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+            fx += __shfl_xor_sync(0xffffffffu, fx, o); fy += __shfl_xor_sync(0xffffffffu, fy, o); fz += __shfl_xor_sync(0xffffffffu, fz, o);
         }
         const int w = threadIdx.x >> 5;
-        if ((threadIdx.x & 31) == 0) { red[w][0] = sx; red[w][1] = sy; red[w][2] = sz; red[w][3] = cnt; }
+        if ((threadIdx.x & 31) == 0) { red[w][0] = fx; red[w][1] = fy; red[w][2] = fz; red[w][3] = (double)(ku * __popc(members)); }
         __syncthreads();
         if (threadIdx.x < 4)
             part[(int64_t)blockIdx.x * 4 + threadIdx.x] = ((red[0][threadIdx.x] + red[1][threadIdx.x]) + red[2][threadIdx.x]) + red[3][threadIdx.x];
@@ -321,11 +346,17 @@ __global__ void __launch_bounds__(128) session_nvt_classify_kernel(Quad4 pos, Qu
     }
 }
 
-// fixed-order reduction of the per-block partial sums into acc (4 doubles)
-__global__ void __launch_bounds__(1024) session_partial_reduce_kernel(const double* __restrict__ part, int64_t blocks, double* __restrict__ acc) {
-    __shared__ double red[32][4];
+// fixed-order reduction of the per-block partial sums into acc (4 doubles): RED_BLOCKS blocks each add up a contiguous
+// slice (fixed order inside the slice), the block that finishes last adds the slice sums in slice order.  Which block
+// that is varies, the order of the additions does not: the result is reproducible.  scratch = RED_BLOCKS*4 doubles + a counter.
+constexpr int RED_BLOCKS = 64;
+__global__ void __launch_bounds__(256) session_partial_reduce_kernel(const double* __restrict__ part, int64_t blocks, double* __restrict__ scratch,
+                                                                     double* __restrict__ acc) {
+    __shared__ double red[8][4];
+    __shared__ bool last;
+    const int64_t per = (blocks + RED_BLOCKS - 1) / RED_BLOCKS, b0 = blockIdx.x * per, b1 = b0 + per < blocks ? b0 + per : blocks;
     double v[4] = {0, 0, 0, 0};
-    for (int64_t b = threadIdx.x; b < blocks; b += 1024) {
+    for (int64_t b = b0 + threadIdx.x; b < b1; b += 256) {
         const double2* p2 = reinterpret_cast<const double2*>(part + b * 4);
         double2 lo = p2[0], hi = p2[1];
         v[0] += lo.x; v[1] += lo.y; v[2] += hi.x; v[3] += hi.y;
@@ -338,10 +369,22 @@ __global__ void __launch_bounds__(1024) session_partial_reduce_kernel(const doub
 #pragma unroll
         for (int c = 0; c < 4; ++c) red[threadIdx.x >> 5][c] = v[c];
     __syncthreads();
+    unsigned* counter = reinterpret_cast<unsigned*>(scratch + RED_BLOCKS * 4);
     if (threadIdx.x < 4) {
         double t = 0;
-        for (int w = 0; w < 32; ++w) t += red[w][threadIdx.x];
+        for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+        scratch[blockIdx.x * 4 + threadIdx.x] = t;
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(counter, 1u) == RED_BLOCKS - 1;
+    __syncthreads();
+    if (last && threadIdx.x < 4) {
+        __threadfence();
+        double t = 0;
+        for (int b = 0; b < RED_BLOCKS; ++b) t += *((volatile double*)(scratch + b * 4 + threadIdx.x));
         acc[threadIdx.x] = t;
+        if (threadIdx.x == 0) *counter = 0;
     }
 }
 
@@ -380,18 +423,49 @@ __global__ void __launch_bounds__(256) session_class_max_kernel(Quad4 pos, const
                                                                 int key, const int32_t* __restrict__ idx, int64_t n, int k, int ku,
                                                                 float* __restrict__ cd) {
     V3 c = v3(cd[0], cd[1], cd[2]);
+    const bool vec = (k & 3) == 0 && (ku & 3) == 0;   // 16-byte loads of the row prefix
     float mx = 0.0f;
     for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += (int64_t)gridDim.x * blockDim.x) {
         if ((owned && !owned[s]) || label[s] != key) continue;
         const int32_t* row = idx + s * k;
-        for (int a = 0; a < ku; ++a) mx = fmaxf(mx, norm3_fma(pos((int64_t)row[a]) - c));
+        if (vec) {
+            const int4* r4 = reinterpret_cast<const int4*>(row);
+            for (int a = 0; a < ku; a += 4) {
+                const int4 q = __ldg(r4 + (a >> 2));
+                mx = fmaxf(fmaxf(mx, norm3_fma(pos((int64_t)q.x) - c)), norm3_fma(pos((int64_t)q.y) - c));
+                mx = fmaxf(fmaxf(mx, norm3_fma(pos((int64_t)q.z) - c)), norm3_fma(pos((int64_t)q.w) - c));
+            }
+        } else {
+            for (int a = 0; a < ku; ++a) mx = fmaxf(mx, norm3_fma(pos((int64_t)row[a]) - c));
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if ((threadIdx.x & 31) == 0) atomicMax((int*)(cd + 3), __float_as_int(mx));
 }
 
+// new position of row s under strategy `kind`.  KU > 0: compile-time row length, ids fetched with 16-byte loads into
+// registers (a scalar load per neighbour id is one L1 tag look-up per LANE, rows being 64 bytes apart); KU = 0: runtime length.
+template <int KU>
+__device__ __forceinline__ V3 session_move_point(int kind, const Quad4& pos, const Quad4& fn, const float4* __restrict__ edge, int64_t s,
+                                                 const int32_t* __restrict__ row, int ku, const float* __restrict__ cd, float alpha, float dmax) {
+    if constexpr (KU > 0) {
+        RowRegs<KU> r;
+        r.load(row);
+        if (kind == NGPD_STEP_FLAT) return flat_point_row<KU>(pos, fn, s, r, KU, cd[3], alpha, dmax);
+        if (kind == NGPD_STEP_EDGE) { float4 e = __ldg(edge + s); return edge_point_row<KU>(pos, fn, v3(e.x, e.y, e.z), s, r, KU, alpha, dmax); }
+        if (kind == NGPD_STEP_FEATURE) return feature_point_row<KU>(pos, fn, s, r, KU, alpha, dmax);
+        return corner_point_row<KU>(pos, fn, s, r, KU, alpha, dmax);
+    } else {
+        if (kind == NGPD_STEP_FLAT) return flat_point(pos, fn, s, row, ku, cd[3], alpha, dmax);
+        if (kind == NGPD_STEP_EDGE) { float4 e = __ldg(edge + s); return edge_point(pos, fn, v3(e.x, e.y, e.z), s, row, ku, alpha, dmax); }
+        if (kind == NGPD_STEP_FEATURE) return feature_point(pos, fn, s, row, ku, alpha, dmax);
+        return corner_point(pos, fn, s, row, ku, alpha, dmax);
+    }
+}
+
 // one class: members move, everybody else is copied through to the other buffer (snapshot semantics)
+template <int KU>
 __global__ void __launch_bounds__(128) session_update_kernel(int kind, int key, Quad4 pos, Quad4 fn, const float4* __restrict__ edge,
                                                              const uint8_t* __restrict__ label, const uint8_t* __restrict__ owned,
                                                              const int32_t* __restrict__ idx, int64_t n, int k, int ku, float alpha, float dmax,
@@ -399,18 +473,14 @@ __global__ void __launch_bounds__(128) session_update_kernel(int kind, int key, 
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     V3 p = pos(s);
-    if (label[s] == key && (!owned || owned[s])) {
-        const int32_t* row = idx + s * k;
-        if (kind == NGPD_STEP_FLAT) p = flat_point(pos, fn, s, row, ku, cd[3], alpha, dmax);
-        else if (kind == NGPD_STEP_EDGE) { float4 e = __ldg(edge + s); p = edge_point(pos, fn, v3(e.x, e.y, e.z), s, row, ku, alpha, dmax); }
-        else if (kind == NGPD_STEP_FEATURE) p = feature_point(pos, fn, s, row, ku, alpha, dmax);
-        else if (kind == NGPD_STEP_CORNER) p = corner_point(pos, fn, s, row, ku, alpha, dmax);
-    }
+    if (label[s] == key && (!owned || owned[s]) && kind >= NGPD_STEP_FLAT && kind <= NGPD_STEP_CORNER)
+        p = session_move_point<KU>(kind, pos, fn, edge, s, idx + s * k, ku, cd, alpha, dmax);
     out[s] = make_float4(p.x, p.y, p.z, 0.0f);
 }
 
 // one minority class, in place: the listed rows move, nothing else is touched.  Two launches because a row's neighbours
 // may be rows of the same class: every new position is computed from the snapshot before any of them is stored.
+template <int KU>
 __global__ void __launch_bounds__(128) session_update_rows_kernel(int kind, Quad4 pos, Quad4 fn, const float4* __restrict__ edge,
                                                                   const int32_t* __restrict__ list, const int32_t* __restrict__ count,
                                                                   const int32_t* __restrict__ idx, int k, int ku, float alpha, float dmax,
@@ -418,12 +488,7 @@ __global__ void __launch_bounds__(128) session_update_rows_kernel(int kind, Quad
     const int cnt = *count;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
         const int64_t s = list[i];
-        const int32_t* row = idx + s * k;
-        V3 p;
-        if (kind == NGPD_STEP_FLAT) p = flat_point(pos, fn, s, row, ku, cd[3], alpha, dmax);
-        else if (kind == NGPD_STEP_EDGE) { float4 e = __ldg(edge + s); p = edge_point(pos, fn, v3(e.x, e.y, e.z), s, row, ku, alpha, dmax); }
-        else if (kind == NGPD_STEP_FEATURE) p = feature_point(pos, fn, s, row, ku, alpha, dmax);
-        else p = corner_point(pos, fn, s, row, ku, alpha, dmax);
+        const V3 p = session_move_point<KU>(kind, pos, fn, edge, s, idx + s * k, ku, cd, alpha, dmax);
         moved[i] = make_float4(p.x, p.y, p.z, 0.0f);
     }
 }
@@ -528,14 +593,25 @@ static void run_knn_tiers(ngpd_session* S, int k, int32_t* idx, cudaStream_t st,
     const float4* p = S->pos[S->cur];
     KnnLists L(S);
     KnnTrack tr{S->cand, S->anchor};
+    uint8_t* late = S->overlap_tail ? S->late : nullptr;
     if (todo)
         session_knn_fast_kernel<K, KT><<<stride_blocks(S->n, KsCfg<1>::THREADS, 16), KsCfg<1>::THREADS, 0, st>>>(
-            g, p, S->owned, S->n, k, idx, tr, L.list[0], L.cnt[0], L.list[1], L.cnt[1]);
+            g, p, S->owned, S->n, k, idx, tr, L.list[0], L.cnt[0], L.list[1], L.cnt[1], late);
     else
         session_knn_fast_kernel<K, KT><<<(unsigned)cdiv(S->n, KsCfg<1>::THREADS), KsCfg<1>::THREADS, 0, st>>>(
-            g, p, S->owned, S->n, k, idx, tr, nullptr, nullptr, L.list[1], L.cnt[1]);
-    session_knn_wide_kernel<K, KT><<<stride_blocks(S->n, KsCfg<2>::THREADS, 16), KsCfg<2>::THREADS, 0, st>>>(g, p, k, idx, tr, L.list[1], L.cnt[1], L.list[2], L.cnt[2]);
-    session_knn_fix_kernel<K, KT><<<stride_blocks(S->n, 128, 8), 128, 0, st>>>(g, p, k, idx, tr, L.list[2], L.cnt[2]);
+            g, p, S->owned, S->n, k, idx, tr, nullptr, nullptr, L.list[1], L.cnt[1], late);
+    cudaStream_t ts = st;
+    if (late) {
+        cudaEventRecord(S->tail_ev[0], st);
+        cudaStreamWaitEvent(S->tail, S->tail_ev[0], 0);
+        ts = S->tail;
+    }
+    session_knn_wide_kernel<K, KT><<<stride_blocks(S->n, KsCfg<2>::THREADS, 16), KsCfg<2>::THREADS, 0, ts>>>(g, p, k, idx, tr, L.list[1], L.cnt[1], L.list[2], L.cnt[2]);
+    session_knn_fix_kernel<K, KT><<<stride_blocks(S->n, 128, 8), 128, 0, ts>>>(g, p, k, idx, tr, L.list[2], L.cnt[2]);
+    if (late) {
+        cudaEventRecord(S->tail_ev[1], S->tail);
+        S->tail_pending = true;
+    }
 }
 
 // `track`: this is the step's own search -- it may answer from, and refreshes, the stored candidates
@@ -606,9 +682,11 @@ using namespace ngpd;
 extern "C" __attribute__((visibility("default"))) int ngpd_session_destroy(ngpd_session_t* S) {
     if (!S) return 0;
     if (S->grid) ngpd_grid_destroy(S->grid);
-    void* bufs[] = {S->pos[0], S->pos[1], S->nrm, S->fn, S->edge, S->label, S->owned, S->idx, S->acc, S->cd, S->fix, S->cand, S->anchor, S->part, S->cls, S->inv, S->stage_pos, S->stage_nrm, S->stage_lab};
+    void* bufs[] = {S->pos[0], S->pos[1], S->nrm, S->fn, S->edge, S->label, S->owned, S->idx, S->acc, S->cd, S->fix, S->cand, S->anchor, S->part, S->red2, S->cls, S->inv, S->stage_pos, S->stage_nrm, S->stage_lab};
     for (void* b : bufs) if (b) cudaFree(b);
     if (S->side) { cudaStreamDestroy(S->side); for (cudaEvent_t e : S->xfer) if (e) cudaEventDestroy(e); }
+    if (S->tail) { cudaStreamDestroy(S->tail); for (cudaEvent_t e : S->tail_ev) if (e) cudaEventDestroy(e); }
+    if (S->late) cudaFree(S->late);
     delete S;
     return 0;
 }
@@ -632,9 +710,11 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_create(const 
     if (e == cudaSuccess) e = cudaMalloc(&S->label, (size_t)n);
     if (e == cudaSuccess) e = cudaMalloc(&S->acc, 4 * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&S->cd, 4 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&S->red2, (RED_BLOCKS * 4 + 1) * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&S->fix, (3 * (size_t)n + 3) * sizeof(int32_t));
     if (e != cudaSuccess) { set_error("ngpd_session_create: %s", cudaGetErrorString(e)); ngpd_session_destroy(S); return -2; }
     NGPD_CUDA_OK(cudaMemsetAsync(S->label, 0, (size_t)n, st));
+    NGPD_CUDA_OK(cudaMemsetAsync(S->red2, 0, (RED_BLOCKS * 4 + 1) * sizeof(double), st));
     NGPD_CUDA_OK(cudaMemsetAsync(S->nrm, 0, b4, st));
     // current positions start as the tree positions
     session_scatter_in_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(G->pts, tree_pos, nullptr, n, S->pos[0], nullptr);
@@ -688,7 +768,19 @@ static int features_knn(ngpd_session_t* S, const ngpd_step_params_t* p, cudaStre
     int rc = ensure_idx(S, kf);
     if (rc) return rc;
     S->idx_k = kf;
+    if (!S->tail) {
+        // highest priority: its few blocks must get SM slots as the tensor pass' blocks retire, not after all of them
+        int prio_lo = 0, prio_hi = 0;
+        NGPD_CUDA_OK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        NGPD_CUDA_OK(cudaStreamCreateWithPriority(&S->tail, cudaStreamNonBlocking, prio_hi));
+        for (cudaEvent_t& e : S->tail_ev) NGPD_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        NGPD_CUDA_OK(cudaMalloc(&S->late, (size_t)S->n));
+        NGPD_CUDA_OK(cudaMemsetAsync(S->late, 0, (size_t)S->n, st));
+    }
+    static const bool tail_off = getenv("NGPD_NO_TAIL_OVERLAP") != nullptr;   // measurements only
+    S->overlap_tail = !tail_off;   // honoured by the tiered search only (5 <= k <= 32, not in exact-only mode)
     { ProfScope ps(S, st, 0); rc = run_knn(S, kf, S->idx, st, true); }
+    S->overlap_tail = false;
     if (rc) return rc;
     S->launches += S->knn_launches;
     return 0;
@@ -699,10 +791,23 @@ static int features_smooth(ngpd_session_t* S, const ngpd_step_params_t* p, cudaS
     Quad4 pos{S->pos[S->cur]};
     { ProfScope ps(S, st, 1);
       Quad4 nq{S->nrm};
-      if (kf == 16) session_nvt_smooth_kernel<16><<<b, 128, 0, st>>>(pos, nq, S->owned, S->idx, S->n, kf, p->x_thresh, p->tau, p->damp, S->fn);
-      else if (kf == 32) session_nvt_smooth_kernel<32><<<b, 128, 0, st>>>(pos, nq, S->owned, S->idx, S->n, kf, p->x_thresh, p->tau, p->damp, S->fn);
-      else if (kf == 8) session_nvt_smooth_kernel<8><<<b, 128, 0, st>>>(pos, nq, S->owned, S->idx, S->n, kf, p->x_thresh, p->tau, p->damp, S->fn);
-      else session_nvt_smooth_kernel<0><<<b, 128, 0, st>>>(pos, nq, S->owned, S->idx, S->n, kf, p->x_thresh, p->tau, p->damp, S->fn); }
+      const uint8_t* late = S->tail_pending ? S->late : nullptr;
+      if (kf == 16) session_nvt_smooth_kernel<16><<<b, 128, 0, st>>>(pos, nq, S->owned, late, S->idx, S->n, kf, p->x_thresh, p->tau, p->damp, S->fn);
+      else if (kf == 32) session_nvt_smooth_kernel<32><<<b, 128, 0, st>>>(pos, nq, S->owned, late, S->idx, S->n, kf, p->x_thresh, p->tau, p->damp, S->fn);
+      else if (kf == 8) session_nvt_smooth_kernel<8><<<b, 128, 0, st>>>(pos, nq, S->owned, late, S->idx, S->n, kf, p->x_thresh, p->tau, p->damp, S->fn);
+      else session_nvt_smooth_kernel<0><<<b, 128, 0, st>>>(pos, nq, S->owned, late, S->idx, S->n, kf, p->x_thresh, p->tau, p->damp, S->fn);
+      if (S->tail_pending) {
+          // the rows the last two search tiers were still working on
+          KnnLists L(S);
+          NGPD_CUDA_OK(cudaStreamWaitEvent(st, S->tail_ev[1], 0));
+          const int lb = stride_blocks(S->n, 128, 8);
+          if (kf == 16) session_nvt_smooth_late_kernel<16><<<lb, 128, 0, st>>>(pos, nq, L.list[1], L.cnt[1], S->late, S->idx, kf, p->x_thresh, p->tau, p->damp, S->fn);
+          else if (kf == 32) session_nvt_smooth_late_kernel<32><<<lb, 128, 0, st>>>(pos, nq, L.list[1], L.cnt[1], S->late, S->idx, kf, p->x_thresh, p->tau, p->damp, S->fn);
+          else if (kf == 8) session_nvt_smooth_late_kernel<8><<<lb, 128, 0, st>>>(pos, nq, L.list[1], L.cnt[1], S->late, S->idx, kf, p->x_thresh, p->tau, p->damp, S->fn);
+          else session_nvt_smooth_late_kernel<0><<<lb, 128, 0, st>>>(pos, nq, L.list[1], L.cnt[1], S->late, S->idx, kf, p->x_thresh, p->tau, p->damp, S->fn);
+          S->tail_pending = false;
+          S->launches += 1;
+      } }
     S->launches += 1;
     NGPD_CUDA_OK(cudaGetLastError());
     return 0;
@@ -753,13 +858,13 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_phase_flat_sc
     Quad4 pos{S->pos[S->cur]};
     ProfScope ps(S, st, 3);
     if (part == 0 && key == 0 && S->sums_ready) {
-        session_partial_reduce_kernel<<<1, 1024, 0, st>>>(S->part, cdiv(S->n, 128), S->acc);
+        session_partial_reduce_kernel<<<RED_BLOCKS, 256, 0, st>>>(S->part, cdiv(S->n, 128), S->red2, S->acc);
         S->launches += 1;
     } else if (part == 0) {
         if (!S->part) NGPD_CUDA_OK(cudaMalloc(&S->part, (size_t)cdiv(S->n, 128) * 4 * sizeof(double)));
         const unsigned blocks = strided(S->n, 256);
         session_class_sum_kernel<<<blocks, 256, 0, st>>>(pos, S->owned, S->label, key, S->idx, S->n, S->idx_k, p->k_update, S->part);
-        session_partial_reduce_kernel<<<1, 1024, 0, st>>>(S->part, (int64_t)blocks, S->acc);
+        session_partial_reduce_kernel<<<RED_BLOCKS, 256, 0, st>>>(S->part, (int64_t)blocks, S->red2, S->acc);
         S->sums_ready = false;
         S->launches += 2;
     } else {
@@ -777,20 +882,30 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_phase_update(
     int kind = p->strategy[key];
     if (kind < 0) return 0;
     ProfScope ps(S, st, 4);
+    const bool fixed8 = p->k_update == 8 && S->idx_k % 4 == 0;   // rows of 8 ids, 16-byte aligned
     if (key > 0 && S->lists_ready) {
         // minority class: its rows only, in place (the other position buffer is free and holds the moved rows in between)
         const int32_t *list = S->cls + (int64_t)(key - 1) * S->n, *count = S->cls + 2 * S->n + (key - 1);
-        session_update_rows_kernel<<<stride_blocks(S->n, 128, 16), 128, 0, st>>>(kind, Quad4{S->pos[S->cur]}, Quad4{S->fn}, S->edge, list, count, S->idx,
-                                                                              S->idx_k, p->k_update, p->alpha[key], p->dmax, S->cd, S->pos[S->cur ^ 1]);
+        if (fixed8)
+            session_update_rows_kernel<8><<<stride_blocks(S->n, 128, 16), 128, 0, st>>>(kind, Quad4{S->pos[S->cur]}, Quad4{S->fn}, S->edge, list, count, S->idx,
+                                                                                     S->idx_k, p->k_update, p->alpha[key], p->dmax, S->cd, S->pos[S->cur ^ 1]);
+        else
+            session_update_rows_kernel<0><<<stride_blocks(S->n, 128, 16), 128, 0, st>>>(kind, Quad4{S->pos[S->cur]}, Quad4{S->fn}, S->edge, list, count, S->idx,
+                                                                                     S->idx_k, p->k_update, p->alpha[key], p->dmax, S->cd, S->pos[S->cur ^ 1]);
         session_apply_rows_kernel<<<stride_blocks(S->n, 256, 8), 256, 0, st>>>(list, count, S->pos[S->cur ^ 1], S->pos[S->cur]);
         NGPD_CUDA_OK(cudaGetLastError());
         S->sums_ready = false;
         S->launches += 2;
         return 0;
     }
-    session_update_kernel<<<(unsigned)cdiv(S->n, 128), 128, 0, st>>>(kind, key, Quad4{S->pos[S->cur]}, Quad4{S->fn}, S->edge, S->label, S->owned,
-                                                                     S->idx, S->n, S->idx_k, p->k_update, p->alpha[key], p->dmax, S->cd,
-                                                                     S->pos[S->cur ^ 1]);
+    if (fixed8)
+        session_update_kernel<8><<<(unsigned)cdiv(S->n, 128), 128, 0, st>>>(kind, key, Quad4{S->pos[S->cur]}, Quad4{S->fn}, S->edge, S->label, S->owned,
+                                                                            S->idx, S->n, S->idx_k, p->k_update, p->alpha[key], p->dmax, S->cd,
+                                                                            S->pos[S->cur ^ 1]);
+    else
+        session_update_kernel<0><<<(unsigned)cdiv(S->n, 128), 128, 0, st>>>(kind, key, Quad4{S->pos[S->cur]}, Quad4{S->fn}, S->edge, S->label, S->owned,
+                                                                            S->idx, S->n, S->idx_k, p->k_update, p->alpha[key], p->dmax, S->cd,
+                                                                            S->pos[S->cur ^ 1]);
     NGPD_CUDA_OK(cudaGetLastError());
     S->cur ^= 1;
     S->sums_ready = false;
@@ -839,7 +954,7 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_mean_edge_len
     int rc = run_knn(S, k, idx, st);
     if (rc) return rc;
     session_edge_len_kernel<<<blocks, 256, 0, st>>>(Quad4{S->pos[S->cur]}, S->owned, idx, S->n, k, part);
-    session_partial_reduce_kernel<<<1, 1024, 0, st>>>(part, (int64_t)blocks, acc);
+    session_partial_reduce_kernel<<<RED_BLOCKS, 256, 0, st>>>(part, (int64_t)blocks, S->red2, acc);
     double h[2];
     NGPD_CUDA_OK(cudaMemcpyAsync(h, acc, sizeof(h), cudaMemcpyDeviceToHost, st));
     NGPD_CUDA_OK(cudaStreamSynchronize(st));

@@ -267,3 +267,27 @@ class SlabSession:
             for t in (full_p, full_n, full_l):
                 dist.all_reduce(t, group=self.group)
         return full_p, full_n, full_l.to(torch.uint8)
+
+    # -- end-to-end step with HOST buffers of the OWNED rows (what bench.py's e2e times on more than one GPU) -----------
+    def step_host(self, pos_host: torch.Tensor, nrm_host: torch.Tensor, pos_out: torch.Tensor, nrm_out: torch.Tensor,
+                  lab_out: torch.Tensor):
+        """One iteration whose inputs and outputs live in pinned host memory: this rank's owned positions / normals
+        ([n_owned,3] fp32, slab order = `plan.owned`) go host -> device, halo copies are refreshed from their owners,
+        the iteration runs with its halo exchanges, and the owned positions / normals / labels come back."""
+        lib, L = self._lib.load(), self._lib
+        h, dev, k = self.session._h, self._send_buf.device, self.n_owned
+        if not hasattr(self, "_owned_rows"):
+            self._owned_rows = self._inv[:k].to(torch.int32).contiguous()       # tree positions of the owned rows
+            self._io4 = torch.zeros((k, 4), dtype=torch.float32, device=dev)
+        rows, io4 = self._owned_rows, self._io4
+        for which, src in ((0, pos_host), (1, nrm_host)):
+            io4[:, :3].copy_(src, non_blocking=True)
+            L.check(lib.ngpd_session_import_rows(h, which, rows.data_ptr(), k, io4.data_ptr(), L.stream()), "ngpd_session_import_rows")
+            self._refresh(which)
+        self.step()
+        for which, dst in ((0, pos_out), (1, nrm_out)):
+            L.check(lib.ngpd_session_export_rows(h, which, rows.data_ptr(), k, io4.data_ptr(), L.stream()), "ngpd_session_export_rows")
+            dst.copy_(io4[:, :3], non_blocking=True)
+        labels = self._scalar_view(5, (self.n_owned + self.n_halo,), "|u1")
+        lab_out.copy_(labels[rows.long()], non_blocking=True)
+        torch.cuda.current_stream().synchronize()

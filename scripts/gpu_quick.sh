@@ -1,6 +1,6 @@
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q -k "rerank or session or denoise or until or labels or generic" > gpurun_out/pytest_q.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_q.log
+timeout 900 python -m pytest tests -m gpu -x -q -k "rerank or session or denoise or until or labels or generic or run_host or phase or one_shot" > gpurun_out/pytest_q.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_q.log
 tail -5 gpurun_out/pytest_q.log
 timeout 600 python bench.py --steps 8 --warmup 3 --no-cpu > gpurun_out/bench_q.json 2> gpurun_out/bench_q.err; echo "bench rc=$?"
 tail -3 gpurun_out/bench_q.err

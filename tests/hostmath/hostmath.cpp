@@ -7,6 +7,7 @@ using std::signbit;
 using std::isfinite;
 #include "../../normal-guided-pointcloud-denoiser_b200/csrc/point_math.cuh"
 #include "eig3_generic.h"
+#include "../../normal-guided-pointcloud-denoiser_b200/csrc/sortnet.cuh"
 
 using namespace ngpd;
 
@@ -92,6 +93,15 @@ void hm_update(int kind, const float* pos, const float* nrm, const float* edge, 
         else p = corner_point(P, N, c, idx + r * k, k, alpha, dmax);
         out[3 * r] = p.x; out[3 * r + 1] = p.y; out[3 * r + 2] = p.z;
     }
+}
+
+// sorting networks of the k-NN selection (csrc/sortnet.cuh): sort / bitonic-merge one array of n = 8, 16 or 32 keys
+int hm_sortnet(unsigned* keys, int n, int bitonic) {
+#define NGPD_SN(N) if (n == N) { unsigned a[N]; for (int i = 0; i < N; ++i) a[i] = keys[i]; \
+        if (bitonic) ks_bitonic_merge<N>(a); else ks_sort<N>(a); for (int i = 0; i < N; ++i) keys[i] = a[i]; return 0; }
+    NGPD_SN(8) NGPD_SN(16) NGPD_SN(32)
+#undef NGPD_SN
+    return -1;
 }
 
 }  // extern "C"

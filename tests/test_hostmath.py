@@ -180,3 +180,32 @@ def test_nvt_weight_shortcut_equals_exact_sequence(hm, thresh):
     assert np.array_equal(ex, qk)
     if 0 < thresh < 1:
         assert 0.05 < ex[h:].mean() < 0.95          # the constructed edges really straddle the threshold
+
+
+def test_sorting_networks_zero_one_principle(hm):
+    """csrc/sortnet.cuh: a comparator network sorts every input iff it sorts every 0/1 input.  All 2^16 inputs of the
+    16-key sorter and all 2^8 of the 8-key one; the 32-key sorter and the bitonic mergers on random and adversarial keys."""
+    rng = np.random.default_rng(0)
+
+    def run(keys, bitonic=False):
+        a = np.ascontiguousarray(keys, dtype=np.uint32)
+        assert hm.hm_sortnet(P(a), len(a), int(bitonic)) == 0
+        return a
+
+    for n in (8, 16):
+        for bits in range(1 << n):
+            v = np.array([(bits >> i) & 1 for i in range(n)], dtype=np.uint32)
+            out = run(v)
+            assert np.array_equal(out, np.sort(v)), (n, bits)
+    for _ in range(2000):
+        v = rng.integers(0, 2 ** 32, 32, dtype=np.uint64).astype(np.uint32)
+        assert np.array_equal(run(v), np.sort(v))
+        v01 = rng.integers(0, 2, 32).astype(np.uint32)
+        assert np.array_equal(run(v01), np.sort(v01))
+    # bitonic merge: ascending run followed by a descending run of any split
+    for n in (8, 16, 32):
+        for split in range(n + 1):
+            for _ in range(50):
+                v = rng.integers(0, 1000, n).astype(np.uint32)
+                v = np.concatenate([np.sort(v[:split]), np.sort(v[split:])[::-1]])
+                assert np.array_equal(run(v, True), np.sort(v)), (n, split)
