@@ -35,6 +35,24 @@ def algorithmic_bytes(k_f=K_F, k_u=K_U):
     }
 
 
+def ncu_traffic(n):
+    """DRAM bytes per launch of the kernels of one group, from the committed `ncu --set full` capture (profiles/ncu_traffic.json:
+    dram__bytes_read.sum + dram__bytes_write.sum per launch and point at the captured size), scaled to n points."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return {}, None
+    t = json.load(open(p))
+    per = {k: sum(v) / len(v) for k, v in t["bytes_per_point"].items()}
+    groups = {"knn": ("session_knn_rerank_kernel", "session_knn_fast_kernel", "session_knn_wide_kernel", "session_knn_fix_kernel"),
+              "nvt_smooth": ("session_nvt_smooth_kernel", "session_nvt_smooth_late_kernel"), "nvt_classify": ("session_nvt_classify_kernel",),
+              "flat_scalars": ("session_partial_reduce_kernel", "session_center_kernel", "session_class_max_kernel")}
+    out = {g: sum(per.get(k, 0.0) for k in ks) * n for g, ks in groups.items()}
+    upd = t["bytes_per_point"]
+    out["update"] = (sum(upd.get("session_update_kernel", [0.0])) + sum(upd.get("session_update_rows_kernel", [0.0])) +
+                     sum(upd.get("session_apply_rows_kernel", [0.0]))) * n
+    return out, f"{t['source']} at {t['points']} points, scaled per point"
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -154,19 +172,22 @@ def run_reference(args):
         pos, nrm, _, _ = O.denoise_iteration(noisy, pos, nrm, K_F, K_U, xt, ALPHAS, d, knn=knn)
     dt = time.perf_counter() - t0
     value = n_sample * args.steps / dt
-    sample = f"{n_sample}-point cloud from the same generator, {args.steps} iterations, SciPy KD-tree with workers=-1"
+    sample = (f"{n_sample}-point cloud from the same generator (the full workload has {args.points} points; throughput per point is "
+              f"size-independent to first order for a KD-tree pipeline), {args.steps} timed iterations of the oracle port "
+              f"(NumPy + SciPy cKDTree workers=-1 + LAPACK via torch, all {cores} host threads)")
     line = {"impl": "reference", "metric": "denoise point-iterations/sec (kNN+NVT+update)", "value": value, "unit": "point-iterations/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, n_sample),
+            "config": workload_config(args, args.points),
             "cpu_baseline": {"value": value, "unit": "point-iterations/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "point-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
 def workload_config(args, n):
-    return {"workload": "config 4: synthetic creased surface (cube faces 60 % + torus 40 %), isotropic Gaussian noise sigma = 0.3 x mean "
-                        "6-NN distance, shuffled; one Processor.denoise iteration body per step",
+    return {"workload": "BASELINE.json configs[3]: synthetic 100M-point noisy CAD-like surface (cube faces 60 % + torus 40 %, isotropic Gaussian noise "
+                        "sigma = 0.3 x mean 6-NN distance, shuffled), k=16/8; one Processor.denoise iteration body per step; the whole cloud "
+                        "fits one B200 (37 GB), more GPUs split the same cloud into Morton slabs",
             "points": n, "k_feature": K_F, "k_update": K_U, "strategy": "flat/edge/feature", "alpha": list(ALPHAS),
             "l2": "inputs larger than L2 (positions+normals+neighbour table >> 126 MB); no flush needed",
             "partition": "single GPU" if args.gpus == 1 else f"{args.gpus} Morton slabs + halo exchange"}
@@ -213,6 +234,7 @@ def run_ours(args):
         dist.barrier()
     profile_src.set_profiling(True)
     profile_src.get_profile()
+    launches_before = profile_src.launch_count()
     sampler = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
@@ -224,7 +246,8 @@ def run_ours(args):
     ms = e0.elapsed_time(e1)
     prof = profile_src.get_profile()
     profile_src.set_profiling(False)
-    launches = profile_src.launch_count()
+    # single GPU: the fused step restarts its counter, so the last step's count x steps; slabs: the phase calls accumulate
+    launches = profile_src.launch_count() * args.steps if world == 1 else profile_src.launch_count() - launches_before
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -290,8 +313,11 @@ def run_ours(args):
                          "achieved_gbs": ab / (per_step * 1e-3) / 1e9, "frac": ab / (per_step * 1e-3) / 1e9 / peak,
                          "share_of_step": per_step / (ms / args.steps)}
     dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
+    traffic, traffic_src = ncu_traffic(n_local)
+    for name in kernels:
+        kernels[name]["ncu_dram_bytes_per_step"] = traffic.get(name)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                "frac": kernels[dom]["frac"], "traffic": traffic.get(dom), "traffic_source": traffic_src, "peak_source": peak_src,
                 "note": "kNN is instruction/latency-bound (register top-k, fp64 distances); reported against HBM as SURVEY 8(d) asks",
                 "iteration_achieved_gbs": bytes_per["iteration"] * n / (ms / args.steps * 1e-3) / 1e9,
                 "iteration_frac": bytes_per["iteration"] * n / (ms / args.steps * 1e-3) / 1e9 / peak}
@@ -304,7 +330,7 @@ def run_ours(args):
     line = {"metric": "denoise point-iterations/sec (kNN+NVT+update)", "value": value, "unit": "point-iterations/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, n), "clocks": clocks,
-            "e2e": e2e, "gpu_launches": launches * args.steps, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu}
+            "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -315,9 +341,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--points", type=int, default=int(os.environ.get("NGPD_BENCH_POINTS", 10_000_000)))
+    ap.add_argument("--points", type=int, default=int(os.environ.get("NGPD_BENCH_POINTS", 100_000_000)))
     ap.add_argument("--cpu-points", type=int, default=200_000)
-    ap.add_argument("--ref-points", type=int, default=100_000)
+    ap.add_argument("--ref-points", type=int, default=400_000)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()

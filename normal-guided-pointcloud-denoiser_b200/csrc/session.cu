@@ -141,7 +141,25 @@ __global__ void __launch_bounds__(128, 4) session_knn_rerank_kernel(GridView g, 
     // (rows that are not this rank's, or past the end, re-rank whatever their column holds -- zeros unless searched before -- and drop the result)
     bool ok = ks_rerank<K>(top, g, KsRowShared<2 * K>{tile, (int)threadIdx.x}, an, q.x, q.y, q.z, ex);
     ok = ok && active && an.w > 0.0f;
-    if (ok) session_write_row<K, KF>(s, k, top.id, idx);
+    if (k == K) {
+        // rows out through the tile as well: the block's 128 rows are one contiguous 128*K*4-byte piece of the table, written
+        // with coalesced 16-byte stores (a lane storing its own 64-byte row touches a cache line per two lanes)
+        __shared__ uint8_t row_ok[128];
+        __syncthreads();                                   // every lane is done reading candidate ids
+#pragma unroll
+        for (int a = 0; a < K; ++a) tile.v[a][threadIdx.x] = top.id[a];
+        row_ok[threadIdx.x] = ok;
+        __syncthreads();
+        constexpr int CH = K / 4;
+        int4* dst = reinterpret_cast<int4*>(idx + row0 * K);
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+            const int c = (int)threadIdx.x + 128 * i, r = c / CH, a0 = (c % CH) * 4;
+            if (row_ok[r]) dst[c] = make_int4(tile.v[a0][r], tile.v[a0 + 1][r], tile.v[a0 + 2][r], tile.v[a0 + 3][r]);
+        }
+    } else if (ok) {
+        session_write_row<K, KF>(s, k, top.id, idx);
+    }
     fix_append(active && !ok, (int)s, fail_list, fail_count);
 }
 

@@ -3,7 +3,7 @@ steady-state iteration (from one re-ranking kernel to the next), their serialise
     python scripts/launch_list_md.py launches.csv [which_step_from_the_end=3]"""
 import csv, sys
 rows = list(csv.reader(open(sys.argv[1])))
-back = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+back = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 for i, r in enumerate(rows):
     if 'Kernel Name' in r:
         h, start = r, i
