@@ -66,6 +66,15 @@ int ngpd_knn(const ngpd_grid_t* grid, const float* query, int64_t m, int k, int 
 int ngpd_nn_sqdist(const ngpd_grid_t* grid, const float* query, int64_t m, int flags,
                    float* d2_out, int32_t* idx_out, void* stream);
 
+/* radius selection: replaces scipy KDTree.query_ball_point(pos, radii) behind Selector.getPointsInRangeSelectionVectorized,
+ * Selector.py:214-229 (the Yadav-2018 baseline path).  Row q = every tree point with fp64 squared
+ * distance <= radii[q]^2, ascending by index (SciPy's order for multi-point queries).  Two passes:
+ *   counting: counts_out[m] != NULL, idx_out == NULL;
+ *   filling:  offsets[m+1] (exclusive scan of the counts, int32) and idx_out[offsets[m]].
+ * flags: NGPD_KNN_QUERY_IS_TREE as in ngpd_knn. */
+int ngpd_ball_query(const ngpd_grid_t* grid, const float* query, int64_t m, const float* radii, int flags,
+                    int32_t* counts_out /*nullable*/, const int32_t* offsets /*nullable*/, int32_t* idx_out /*nullable*/, void* stream);
+
 /* ---- neighbourhood kernels.  Row r describes centre point `rows ? rows[r] : r` with neighbours
  * idx[offsets ? offsets[r] .. offsets[r+1] : r*k .. r*k+k) (CSR when offsets != NULL). -------------------- */
 
@@ -83,6 +92,17 @@ int ngpd_pca_normals(const float* pos, const int32_t* idx, const int32_t* offset
 int ngpd_nvt(const float* pos, const float* nrm, const int32_t* idx, const int32_t* offsets, const int32_t* rows,
              int64_t m, int k, float x_thresh, float* eigval_out, float* eigvec_out,
              float* tensor_out /*nullable*/, int32_t* sumw_out /*nullable*/, void* stream);
+
+/* Decompositionor.getNormalFilteredNVT / getNormalFilteredPVT, Decompositionor.py:260-276, 172-211 (Yadav-2018 baseline):
+ * neighbour j of centre i counts iff acos(clamp(ni.nj)) <= rho, passed as x_le = smallest fp32 x with acos(x) <= rho.
+ * NVT: T = sum w nj nj^T / sum w (nobody passes: ni ni^T).  PVT: covariance of the passing neighbours about their own
+ * mean (nobody passes: all neighbours; empty row: the reference's four-sample surrogate).  Outputs as ngpd_nvt. */
+int ngpd_nvt_normal(const float* nrm, const int32_t* idx, const int32_t* offsets, const int32_t* rows, int64_t m, int k,
+                    float x_le, float* eigval_out, float* eigvec_out, float* tensor_out /*nullable*/, int32_t* sumw_out /*nullable*/,
+                    void* stream);
+int ngpd_pvt_normal(const float* pos, const float* nrm, const int32_t* idx, const int32_t* offsets, const int32_t* rows,
+                    int64_t m, int k, float x_le, float* eigval_out, float* eigvec_out, float* tensor_out /*nullable*/,
+                    int32_t* sumw_out /*nullable*/, void* stream);
 
 /* torch.linalg.eigh on a stack of symmetric 3x3 fp32 tensors (lower triangle read), LAPACK ssyevd order
  * of operations and sign convention (Decompositionor.py:300). */

@@ -79,3 +79,35 @@ class Decompositionor:
                                         _lib.acos_threshold(rho), _lib.ptr(eigval), _lib.ptr(eigvec), None, None, _lib.stream()),
                    "ngpd_nvt")
         return Decomposition(eigval, eigvec)
+
+    def _normal_filtered(self, which: str, selection: Selection, _n: torch.Tensor, rho: float) -> Decomposition:
+        pos = _lib.dev(self.graph.pos, torch.float32, "graph.pos")
+        nrm = _lib.dev(_n, torch.float32, "n")
+        m = len(selection)
+        rows = selection.i.to(torch.int32).contiguous()
+        k = selection.uniform_k()
+        if k is not None:
+            idx, off = selection.table(), None
+        else:
+            idx, off = selection.csr()
+            k = 0
+        eigval = torch.empty((m, 3), dtype=torch.float32, device=pos.device)
+        eigvec = torch.empty((m, 3, 3), dtype=torch.float32, device=pos.device)
+        lib, x_le = _lib.load(), _lib.acos_threshold_le(rho)
+        if which == "nvt":
+            _lib.check(lib.ngpd_nvt_normal(_lib.ptr(nrm), _lib.ptr(idx), _lib.ptr(off), _lib.ptr(rows), m, k, x_le, _lib.ptr(eigval),
+                                           _lib.ptr(eigvec), None, None, _lib.stream()), "ngpd_nvt_normal")
+        else:
+            _lib.check(lib.ngpd_pvt_normal(_lib.ptr(pos), _lib.ptr(nrm), _lib.ptr(idx), _lib.ptr(off), _lib.ptr(rows), m, k, x_le,
+                                           _lib.ptr(eigval), _lib.ptr(eigvec), None, None, _lib.stream()), "ngpd_pvt_normal")
+        return Decomposition(eigval, eigvec)
+
+    def getNormalFilteredNVT(self, selection: Selection, _n: torch.Tensor, rho: float = 0.9) -> Decomposition:
+        """Yadav-2018 normal voting tensor: neighbours whose normal is within rho of the centre's vote (Decompositionor.py:260-276)."""
+        return self._normal_filtered("nvt", selection, _n, rho)
+
+    def getNormalFilteredPVT(self, selection: Selection, _n: torch.Tensor, rho: float = 0.9) -> Decomposition:
+        """Yadav-2018 point voting tensor: covariance of the neighbours whose normal is within rho of the centre's,
+        about their own mean, with the reference's fall-backs (Decompositionor.py:172-211)."""
+        return self._normal_filtered("pvt", selection, _n, rho)
+

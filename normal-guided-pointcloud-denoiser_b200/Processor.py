@@ -48,6 +48,25 @@ class Processor:
         return float(torch.tensor(s / c, dtype=torch.float32))
 
     # ---- reference interface ----------------------------------------------------------------------------
+    def getVUDecomposition(self):
+        """(:83-99) Yadav-2018 feature decomposition at r = 2 x mean 6-NN edge length, rho = 0.95."""
+        g = self.graph
+        g.edge_index = self.graphBuilder.getKNNEdgeIndex(6)
+        r = 2 * TorchUtils.averageEdgeLength(g.pos, g.edge_index)
+        selection = self.selector.getPointsInRangeSelection(float(r))
+        nvt = self.decompositionor.getNormalFilteredNVT(selection, g.n, rho=0.95)
+        filtered_normals = nvt.getVUSmoothedNormals(g.n, tau=0.3, d=3)
+        return self.decompositionor.getNormalFilteredPVT(selection, filtered_normals, rho=0.95)
+
+    def getMartinFeatureDecomposition(self, r: float, rho: float = 0.9):
+        """(:101-108) radius selection -> normal-filtered NVT -> eigen-space smoothing -> normal-filtered PVT."""
+        n = self.graph.n
+        selection = self.selector.getPointsInRangeSelection(float(r))
+        nvt = self.decompositionor.getNormalFilteredNVT(selection, n, rho)
+        filtered_normals = nvt.getVUSmoothedNormals(n)
+        decomposition = self.decompositionor.getNormalFilteredPVT(selection, filtered_normals, rho)
+        return decomposition, filtered_normals
+
     def getMyFeatureDecomposition(self, N: int = 2 ** 4, angle: float = None):
         """(:110-117) NVT on the current normals -> eigen-space smoothing -> NVT on the smoothed normals."""
         angle = angle if angle is not None else math.pi * 5 / 12

@@ -112,6 +112,30 @@ class Selector:
             self._grids[bucket] = _lib.Grid(self.tree_pos, k_hint=bucket)
         return self._grids[bucket]
 
+    def getPointsInRangeSelectionVectorized(self, radii: torch.Tensor, indices: torch.Tensor = None) -> Selection:
+        """Every construction-time point within radii[r] of the CURRENT position of (selected) point r, ascending by
+        index -- scipy's query_ball_point on the frozen tree (Selector.py:214-229)."""
+        from .Utils import TorchUtils
+        TorchUtils.validateIndices(indices)
+        pos = self.graph.pos
+        N = pos.size(0) if indices is None else indices.size(0)
+        assert radii.dim() == 1
+        assert radii.size(0) == N, f"Actual: {radii.size(0)}\nExpected: {N}"
+        assert radii.is_floating_point()
+        flags = 0
+        if indices is None:
+            query = pos
+            flags = _lib.KNN_QUERY_IS_TREE if pos.size(0) == self.tree_pos.size(0) else 0
+            indices = torch.arange(N, dtype=torch.long, device=pos.device)
+        else:
+            query = pos[indices]
+        j, off = self._grid(16).ball(query, radii.to(device=pos.device, dtype=torch.float32), flags)
+        return Selection(indices, j.long(), off.long())
+
+    def getPointsInRangeSelection(self, radius: float, indices: torch.Tensor = None) -> Selection:
+        n = self.graph.pos.size(0) if indices is None else indices.size(0)
+        return self.getPointsInRangeSelectionVectorized(torch.full((n,), float(radius), dtype=torch.float32, device=self.graph.pos.device), indices)
+
     def getKNNSelection(self, k: int, indices: torch.Tensor = None) -> Selection:
         """k nearest construction-time points of the CURRENT position of every (selected) point, self included,
         ascending by distance (Selector.py:235-246)."""

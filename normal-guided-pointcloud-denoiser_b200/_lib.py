@@ -37,6 +37,9 @@ SIGNATURES = {
     "ngpd_grid_order": (ctypes.c_int, [c_vp, c_vp, c_vp]),
     "ngpd_knn": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.c_int, ctypes.c_int, c_vp, c_vp, c_vp]),
     "ngpd_nn_sqdist": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.c_int, c_vp, c_vp, c_vp]),
+    "ngpd_ball_query": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, ctypes.c_int, c_vp, c_vp, c_vp, c_vp]),
+    "ngpd_nvt_normal": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.c_int, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "ngpd_pvt_normal": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.c_int, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ngpd_pca_normals": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, ctypes.c_int, c_vp, c_vp, c_vp, c_vp]),
     "ngpd_nvt": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.c_int, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ngpd_eigh3": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
@@ -157,6 +160,23 @@ class Grid:
             check(load().ngpd_knn(self._h, ptr(query), m, k, flags, ptr(idx), ptr(d2), stream()), "ngpd_knn")
         return (idx, d2) if with_d2 else idx
 
+    def ball(self, query: torch.Tensor, radii: torch.Tensor, flags: int = 0):
+        """(idx int32 [total], offsets int32 [m+1]): per query every tree point within its radius, ascending by index"""
+        q = dev(query, torch.float32, "query")
+        r = dev(radii, torch.float32, "radii")
+        m = q.size(0)
+        assert r.dim() == 1 and r.size(0) == m
+        counts = torch.empty(m, dtype=torch.int32, device=q.device)
+        check(load().ngpd_ball_query(self._h, ptr(q), m, ptr(r), flags, ptr(counts), None, None, stream()), "ngpd_ball_query")
+        total = int(counts.sum(dtype=torch.int64).item())
+        if total >= 2 ** 31:
+            raise NgpdError(f"ngpd_ball_query: {total} neighbours do not fit the int32 offsets of the neighbourhood kernels")
+        offsets = torch.zeros(m + 1, dtype=torch.int32, device=q.device)
+        offsets[1:] = torch.cumsum(counts, 0, dtype=torch.int64).to(torch.int32)
+        idx = torch.empty(max(total, 1), dtype=torch.int32, device=q.device)
+        check(load().ngpd_ball_query(self._h, ptr(q), m, ptr(r), flags, None, ptr(offsets), ptr(idx), stream()), "ngpd_ball_query")
+        return idx[:total], offsets
+
     def nn_sqdist(self, query: torch.Tensor, want_idx: bool = False, flags: int = 0):
         query = dev(query, torch.float32, "query")
         m = query.size(0)
@@ -200,6 +220,33 @@ def acos_threshold(rho: float) -> float:
             val = float(lo)
         _THRESH_CACHE[rho] = val
     return _THRESH_CACHE[rho]
+
+
+def acos_threshold_le(rho: float) -> float:
+    """Smallest fp32 x in [-1, 1] with torch-CPU acos(x) <= rho: `acos(clamp(ni.nj)) <= rho` (Decompositionor.py:185,
+    271) becomes `clamp(ni.nj) >= x`.  2.0 when nothing passes (rho < 0)."""
+    key = ("le", float(rho))
+    if key not in _THRESH_CACHE:
+        import numpy as np
+
+        def passes(x):
+            return bool((torch.tensor([x], dtype=torch.float32).acos() <= float(rho)).item())
+
+        lo, hi = np.float32(-1.0), np.float32(1.0)       # passes(hi) is acos(1) = 0 <= rho
+        if not passes(1.0):
+            val = 2.0
+        elif passes(-1.0):
+            val = -1.0
+        else:
+            while np.nextafter(lo, np.float32(2.0)) < hi:
+                mid = np.float32((np.float64(lo) + np.float64(hi)) / 2)
+                if passes(float(mid)):
+                    hi = mid
+                else:
+                    lo = mid
+            val = float(hi)
+        _THRESH_CACHE[key] = val
+    return _THRESH_CACHE[key]
 
 
 class Session:

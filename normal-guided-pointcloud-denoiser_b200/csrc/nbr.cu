@@ -54,6 +54,30 @@ __global__ void __launch_bounds__(128) nvt_kernel(Packed3 pos, Packed3 nrm, cons
     if (sumw) sumw[r] = o.sumw;
 }
 
+// Yadav-2018 baseline tensors: neighbours filtered by the angle between the normals.  mode 0 = getNormalFilteredNVT,
+// mode 1 = getNormalFilteredPVT (Decompositionor.py:260-276, 172-211)
+__global__ void __launch_bounds__(128) normal_filtered_kernel(int mode, Packed3 pos, Packed3 nrm, const int32_t* __restrict__ idx,
+                                                              const int32_t* __restrict__ offsets, const int32_t* __restrict__ rows, int64_t m, int k,
+                                                              float x_le, float* __restrict__ eigval, float* __restrict__ eigvec,
+                                                              float* __restrict__ tensor, int32_t* __restrict__ sumw) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    RowSpan s = row_span(r, idx, offsets, rows, k);
+    NvtResult o;
+    float t6[6];
+    if (mode == 0) nvt_normal_point(nrm, s.centre, s.nbr, s.cnt, x_le, o, t6);
+    else pvt_normal_point(pos, nrm, s.centre, s.nbr, s.cnt, x_le, o, t6);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) eigval[3 * r + c] = o.w[c];
+#pragma unroll
+    for (int c = 0; c < 9; ++c) eigvec[9 * r + c] = o.V[c];
+    if (tensor) {
+        float* T = tensor + 9 * r;
+        T[0] = t6[0]; T[1] = t6[1]; T[2] = t6[2]; T[3] = t6[1]; T[4] = t6[3]; T[5] = t6[4]; T[6] = t6[2]; T[7] = t6[4]; T[8] = t6[5];
+    }
+    if (sumw) sumw[r] = o.sumw;
+}
+
 __global__ void __launch_bounds__(128) eigh3_kernel(const float* __restrict__ T, int64_t m, float* __restrict__ eigval, float* __restrict__ eigvec) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= m) return;
@@ -173,6 +197,27 @@ extern "C" __attribute__((visibility("default"))) int ngpd_nvt(const float* pos,
     if (m <= 0) return 0;
     nvt_kernel<<<grid_for(m, 128), 128, 0, (cudaStream_t)stream>>>(Packed3{pos}, Packed3{nrm}, idx, offsets, rows, m, k, x_thresh,
                                                                   eigval_out, eigvec_out, tensor_out, sumw_out);
+    NGPD_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int ngpd_nvt_normal(const float* nrm, const int32_t* idx, const int32_t* offsets, const int32_t* rows, int64_t m, int k,
+                               float x_le, float* eigval_out, float* eigvec_out, float* tensor_out, int32_t* sumw_out, void* stream) {
+    NGPD_REQUIRE(nrm && idx && eigval_out && eigvec_out, "ngpd_nvt_normal: NULL argument");
+    if (m <= 0) return 0;
+    normal_filtered_kernel<<<grid_for(m, 128), 128, 0, (cudaStream_t)stream>>>(0, Packed3{nrm}, Packed3{nrm}, idx, offsets, rows, m, k, x_le, eigval_out,
+                                                                              eigvec_out, tensor_out, sumw_out);
+    NGPD_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int ngpd_pvt_normal(const float* pos, const float* nrm, const int32_t* idx, const int32_t* offsets, const int32_t* rows,
+                               int64_t m, int k, float x_le, float* eigval_out, float* eigvec_out, float* tensor_out, int32_t* sumw_out,
+                               void* stream) {
+    NGPD_REQUIRE(pos && nrm && idx && eigval_out && eigvec_out, "ngpd_pvt_normal: NULL argument");
+    if (m <= 0) return 0;
+    normal_filtered_kernel<<<grid_for(m, 128), 128, 0, (cudaStream_t)stream>>>(1, Packed3{pos}, Packed3{nrm}, idx, offsets, rows, m, k, x_le, eigval_out,
+                                                                              eigvec_out, tensor_out, sumw_out);
     NGPD_CUDA_OK(cudaGetLastError());
     return 0;
 }

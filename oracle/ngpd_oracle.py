@@ -273,10 +273,11 @@ def flat_center_delta(pos, nbr):
     return c, F32(delta)
 
 
-def flat_step(pos, nrm, rows, nbr, dmax, alpha):
-    """Denoiser.flat_step, Denoiser.py:90-119."""
+def flat_step(pos, nrm, rows, nbr, dmax, alpha, delta=None):
+    """Denoiser.flat_step, Denoiser.py:90-119.  (delta: the cloud-wide radius when `nbr` is only part of the selection.)"""
     pos = np.asarray(pos, dtype=F32); nrm = np.asarray(nrm, dtype=F32)
-    _, delta = flat_center_delta(pos, nbr)
+    if delta is None:
+        _, delta = flat_center_delta(pos, nbr)
     vi = pos[rows]; ni = nrm[rows]
     vj = pos[nbr]; nj = nrm[nbr]
     dist = (vj - vi[:, None]).astype(F32)
@@ -494,3 +495,172 @@ def denoise(tree, pos, nrm, iterations=2, k_f=16, k_u=8, rho=5 * math.pi / 12, k
     for _ in range(iterations):
         pos, nrm, labels, _ = denoise_iteration(tree, pos, nrm, k_f, k_u, x_thresh, dmax=d, knn=knn, **kw)
     return pos, nrm, labels
+
+
+# ------------------------------------------------------------------------------------------------
+# Yadav-2018 baseline path ("CPSD"): radius selection, normal-filtered NVT / PVT, VU labels
+# ------------------------------------------------------------------------------------------------
+def ball_selection(tree: np.ndarray, query: np.ndarray, radii, chunk: int = 1024):
+    """Selector.getPointsInRangeSelectionVectorized, Selector.py:214-229 = scipy KDTree.query_ball_point(query, radii):
+    per query every tree point with fp64 ((dx^2+dy^2)+dz^2) <= r^2 (r upcast from fp32), ascending by index (SciPy sorts
+    multi-point queries).  Returns (j int64 [total], slices int64 [m+1])."""
+    t = np.asarray(tree, dtype=F32).astype(np.float64)
+    q = np.asarray(query, dtype=F32).astype(np.float64)
+    r = np.broadcast_to(np.asarray(radii, dtype=F32), (len(q),)).astype(np.float64)
+    rows = []
+    for s in range(0, len(q), chunk):
+        d = q[s:s + chunk, None, :] - t[None, :, :]
+        d2 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
+        inside = d2 <= (r[s:s + chunk] * r[s:s + chunk])[:, None]
+        rows.extend(np.nonzero(row)[0] for row in inside)
+    slices = np.zeros(len(q) + 1, dtype=np.int64)
+    slices[1:] = np.cumsum([len(x) for x in rows])
+    j = np.concatenate(rows).astype(np.int64) if rows else np.zeros(0, np.int64)
+    return j, slices
+
+
+def acos_threshold_le(rho: float) -> np.float32:
+    """Smallest fp32 x with torch.acos(x) <= rho: `acos(clamp(ni.nj)) <= rho` <=> `clamp(ni.nj) >= x`."""
+    import torch
+
+    def passes(x):
+        return bool((torch.tensor([x], dtype=torch.float32).acos() <= rho).item())
+
+    lo, hi = F32(-1.0), F32(1.0)
+    if not passes(1.0):
+        return F32(2.0)
+    if passes(-1.0):
+        return F32(-1.0)
+    while np.nextafter(lo, F32(2.0)) < hi:
+        mid = F32((np.float64(lo) + np.float64(hi)) / 2)
+        if passes(float(mid)):
+            hi = mid
+        else:
+            lo = mid
+    return hi
+
+
+def _rows_by_length(slices):
+    """ragged CSR rows grouped by length: yields (row ids, [len(rows), L] positions into j)"""
+    lens = np.diff(slices)
+    for L in np.unique(lens):
+        rows = np.nonzero(lens == L)[0]
+        yield rows, int(L), slices[rows][:, None] + np.arange(int(L))[None, :]
+
+
+def nvt_normal_filtered(nrm, centres, j, slices, x_le):
+    """Decompositionor.getNormalFilteredNVT, Decompositionor.py:260-276.  Returns (eigval, eigvec, T, sum w)."""
+    nrm = np.asarray(nrm, dtype=F32)
+    m = len(slices) - 1
+    T = np.zeros((m, 3, 3), dtype=F32)
+    sw = np.zeros(m, dtype=np.int64)
+    for rows, L, at in _rows_by_length(slices):
+        ni = nrm[centres[rows]]
+        if L == 0:
+            T[rows] = (ni[:, :, None] * ni[:, None, :]).astype(F32)
+            continue
+        nj = nrm[j[at]]
+        w = np.clip(dot3(ni[:, None, :], nj), F32(-1), F32(1)) >= x_le
+        outer = (nj[:, :, :, None] * nj[:, :, None, :]).astype(F32) * w[:, :, None, None].astype(F32)
+        cnt = w.sum(axis=1)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            Tr = (_seq_sum(outer) / cnt.astype(F32)[:, None, None]).astype(F32)
+        none = cnt == 0
+        Tr[none] = (ni[none][:, :, None] * ni[none][:, None, :]).astype(F32)
+        T[rows] = Tr
+        sw[rows] = cnt
+    w_, V_ = eigh3(T)
+    return w_, V_, T, sw
+
+
+def pvt_normal_filtered(pos, nrm, centres, j, slices, x_le):
+    """Decompositionor.getNormalFilteredPVT, Decompositionor.py:172-211.  Returns (eigval, eigvec, C, sum w)."""
+    pos = np.asarray(pos, dtype=F32); nrm = np.asarray(nrm, dtype=F32)
+    m = len(slices) - 1
+    C = np.zeros((m, 3, 3), dtype=F32)
+    sw = np.zeros(m, dtype=np.int64)
+    for rows, L, at in _rows_by_length(slices):
+        ni = nrm[centres[rows]]
+        if L == 0:
+            v = pos[centres[rows]]
+            s1 = np.cross(ni, v).astype(F32)
+            s2 = np.cross(ni, s1).astype(F32)
+            acc = np.zeros((len(rows), 3, 3), dtype=F32)
+            for smp in (s1, -s1, s2, -s2):
+                acc = (acc + (smp[:, :, None] * smp[:, None, :]).astype(F32)).astype(F32)
+            C[rows] = acc
+            continue
+        nj = nrm[j[at]]; vj = pos[j[at]]
+        w = np.clip(dot3(ni[:, None, :], nj), F32(-1), F32(1)) >= x_le
+        w[~w.any(axis=1)] = True                                      # :186-189
+        cnt = w.sum(axis=1)
+        wf = w[:, :, None].astype(F32)
+        c = (_seq_sum((vj * wf).astype(F32)) / cnt.astype(F32)[:, None]).astype(F32)
+        dv = (vj - c[:, None, :]).astype(F32)
+        outer = (dv[:, :, :, None] * dv[:, :, None, :]).astype(F32) * w[:, :, None, None].astype(F32)
+        C[rows] = (_seq_sum(outer) / cnt.astype(F32)[:, None, None]).astype(F32)
+        sw[rows] = cnt
+    w_, V_ = eigh3(C)
+    return w_, V_, C, sw
+
+
+def vu_features(eigval, tau):
+    """Decomposition.getVUFeatures, Decompositionor.py:84-85."""
+    return ((np.asarray(eigval, dtype=F32) < F32(tau)).sum(axis=1) % 3).astype(np.int64)
+
+
+def csr_step(kind, pos, nrm, centres, j, slices, dmax, alpha, edge_vec=None):
+    """One Denoiser step on ragged rows (Selection.filter of a radius selection): dense step per row length; flat_step's
+    cloud-wide centre / delta (Denoiser.py:106-107) is taken over ALL rows first."""
+    pos = np.asarray(pos, dtype=F32)
+    out = np.zeros((len(slices) - 1, 3), dtype=F32)
+    delta = None
+    if kind == "flat":
+        _, delta = flat_center_delta(pos, j)
+    for rows, L, at in _rows_by_length(slices):
+        c, nb = centres[rows], j[at]
+        if L == 0:
+            out[rows] = pos[c]
+            continue
+        if kind == "flat":
+            out[rows] = flat_step(pos, nrm, c, nb, dmax, alpha, delta=delta)
+        elif kind == "edge":
+            out[rows] = edge_step(pos, nrm, edge_vec, c, nb, dmax, alpha)
+        elif kind == "corner":
+            out[rows] = corner_step(pos, nrm, c, nb, dmax, alpha)
+        else:
+            out[rows] = feature_step(pos, nrm, c, nb, dmax, alpha)
+    return out
+
+
+def cpsd_iteration(tree, pos, nrm, original_pos, d, rho=0.9, tau=0.3, alphas=(0.1, 1.0, 1.0), k_u=8, knn=None):
+    """One iteration of the notebook's "CPSD" loop (PostProcessing.ipynb#c9, j == 1): Martin feature decomposition at radius d,
+    VU labels, the three class steps computed from the SAME snapshot (unlike Processor.denoise), accepted where the point
+    stays within d of its original position.  Returns (new positions, smoothed normals, labels, temp positions)."""
+    knn = knn or knn_kdtree
+    pos = np.asarray(pos, dtype=F32); nrm = np.asarray(nrm, dtype=F32)
+    n = len(pos)
+    centres = np.arange(n)
+    j, slices = ball_selection(tree, pos, np.full(n, F32(d), dtype=F32))
+    x_le = acos_threshold_le(rho)
+    w1, V1, _, _ = nvt_normal_filtered(nrm, centres, j, slices, x_le)
+    f_n = smooth_normals(w1, V1, nrm)
+    w2, V2, _, _ = pvt_normal_filtered(pos, f_n, centres, j, slices, x_le)
+    lab = vu_features(w2, tau)
+    nb8 = knn(tree, pos, k_u)
+    temp = pos.copy()
+    big = F32(d) * F32(20000)
+    for key in range(3):
+        rows = np.nonzero(lab == key)[0]
+        if len(rows) == 0:
+            continue
+        if key == 0:
+            temp[rows] = flat_step(pos, f_n, rows, nb8[rows], big, alphas[0])
+        elif key == 1:
+            temp[rows] = edge_step(pos, f_n, V2[:, :, 0], rows, nb8[rows], big, alphas[1])
+        else:
+            temp[rows] = corner_step(pos, f_n, rows, nb8[rows], big, alphas[2])
+    mask = norm3((temp - np.asarray(original_pos, dtype=F32)).astype(F32)) < F32(d)
+    new = pos.copy()
+    new[mask] = temp[mask]
+    return new, f_n, lab, temp

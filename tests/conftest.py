@@ -32,6 +32,13 @@ def cube():
     return dict(np.load(os.path.join(GOLDEN, "cube386_labels.npz")))
 
 
+@pytest.fixture(scope="session")
+def cpsd():
+    """Yadav-2018 baseline path on fandisk, recorded from the reference (tests/golden/make_golden_cpsd.py)"""
+    import numpy as np
+    return dict(np.load(os.path.join(GOLDEN, "cpsd_fandisk.npz")))
+
+
 def angle_between(a, b):
     """fp64 atan2(|a x b|, a.b): fp32 acos has a ~5e-4 rad floor near 0."""
     import numpy as np

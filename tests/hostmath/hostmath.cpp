@@ -95,6 +95,25 @@ void hm_update(int kind, const float* pos, const float* nrm, const float* edge, 
     }
 }
 
+// Yadav-2018 baseline tensors on CSR rows: mode 0 = normal-filtered NVT, 1 = normal-filtered PVT
+void hm_normal_filtered(int mode, const float* pos, const float* nrm, const int32_t* idx, const int32_t* offsets, int64_t m, float x_le,
+                        float* w, float* V, float* T, int32_t* sumw) {
+    HostPacked3 P{pos}, N{nrm};
+    for (int64_t r = 0; r < m; ++r) {
+        NvtResult o;
+        float t6[6];
+        const int32_t* row = idx + offsets[r];
+        const int cnt = offsets[r + 1] - offsets[r];
+        if (mode == 0) nvt_normal_point(N, r, row, cnt, x_le, o, t6);
+        else pvt_normal_point(P, N, r, row, cnt, x_le, o, t6);
+        for (int c = 0; c < 3; ++c) w[3 * r + c] = o.w[c];
+        for (int c = 0; c < 9; ++c) V[9 * r + c] = o.V[c];
+        float* t = T + 9 * r;
+        t[0] = t6[0]; t[1] = t6[1]; t[2] = t6[2]; t[3] = t6[1]; t[4] = t6[3]; t[5] = t6[4]; t[6] = t6[2]; t[7] = t6[4]; t[8] = t6[5];
+        sumw[r] = o.sumw;
+    }
+}
+
 // sorting networks of the k-NN selection (csrc/sortnet.cuh): sort / bitonic-merge one array of n = 8, 16 or 32 keys
 int hm_sortnet(unsigned* keys, int n, int bitonic) {
 #define NGPD_SN(N) if (n == N) { unsigned a[N]; for (int i = 0; i < N; ++i) a[i] = keys[i]; \

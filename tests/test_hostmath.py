@@ -209,3 +209,31 @@ def test_sorting_networks_zero_one_principle(hm):
                 v = rng.integers(0, 1000, n).astype(np.uint32)
                 v = np.concatenate([np.sort(v[:split]), np.sort(v[split:])[::-1]])
                 assert np.array_equal(run(v, True), np.sort(v)), (n, split)
+
+
+def test_cpsd_normal_filtered_tensors(hm, cpsd):
+    """csrc/point_math.cuh nvt_normal_point / pvt_normal_point (Yadav-2018 baseline) on the reference's radius selection:
+    tensors and eigenvalues against the reference's own (recorded) ones."""
+    n = len(cpsd["pos0"])
+    x_le = ctypes.c_float(float(O.acos_threshold_le(0.9)))
+    for it in range(2):
+        t = f"it{it}_"
+        j = np.ascontiguousarray(cpsd[t + "ball_j"], dtype=np.int32)
+        off = np.ascontiguousarray(cpsd[t + "ball_slices"], dtype=np.int32)
+        for mode, nrm_key, T_key, w_key, V_key in ((0, "n_in", "T_nvt", "nvt_eigval", "nvt_eigvec"), (1, "f_n", "T_pvt", "pvt_eigval", "pvt_eigvec")):
+            pos = np.ascontiguousarray(cpsd[t + "pos_in"], dtype=np.float32)
+            nrm = np.ascontiguousarray(cpsd[t + nrm_key], dtype=np.float32)
+            w = np.empty((n, 3), np.float32); V = np.empty((n, 3, 3), np.float32); T = np.empty((n, 3, 3), np.float32)
+            sw = np.empty(n, np.int32)
+            hm.hm_normal_filtered(mode, P(pos), P(nrm), P(j), P(off), ctypes.c_int64(n), x_le, P(w), P(V), P(T), P(sw))
+            ref_T, ref_w = cpsd[t + T_key], cpsd[t + w_key]
+            if mode == 0:
+                assert np.array_equal(T, ref_T)
+            else:
+                assert np.abs(T - ref_T).max() <= 2e-6 * np.abs(ref_T).max()
+            assert np.abs(w - ref_w).max() <= 2e-6 * np.abs(ref_w).max()
+            # eigenvectors up to sign where the spectrum is well separated
+            gap = np.minimum(ref_w[:, 1] - ref_w[:, 0], ref_w[:, 2] - ref_w[:, 1]) / np.abs(ref_w).max()
+            ok = gap > 1e-3
+            dots = np.abs((V * cpsd[t + V_key]).sum(axis=1))
+            assert (dots[ok] > 1 - 1e-4).all()

@@ -149,3 +149,61 @@ def test_cube_labels(cube):
     w2, _, f, _ = O.feature_decomposition(pos, nrm, nbr, xt)
     assert np.array_equal(O.classes(w2), cube["classes"])
     assert angle_between(f, cube["f_n"]).max() < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------------
+# Yadav-2018 baseline path ("CPSD") against vectors recorded from the reference
+# (tests/golden/make_golden_cpsd.py)
+# ------------------------------------------------------------------------------------------------------
+def test_cpsd_ball_selection(cpsd):
+    for it in range(2):
+        j, slices = O.ball_selection(cpsd["pos0"], cpsd[f"it{it}_pos_in"], np.full(len(cpsd["pos0"]), cpsd["d"], np.float32))
+        assert np.array_equal(slices, cpsd[f"it{it}_ball_slices"])
+        assert np.array_equal(j, cpsd[f"it{it}_ball_j"])
+
+
+def test_cpsd_tensors_normals_labels(cpsd):
+    n = len(cpsd["pos0"])
+    x_le = O.acos_threshold_le(0.9)
+    for it in range(3):
+        t = f"it{it}_"
+        j, slices = cpsd[t + "ball_j"].astype(np.int64), cpsd[t + "ball_slices"]
+        w1, V1, T1, _ = O.nvt_normal_filtered(cpsd[t + "n_in"], np.arange(n), j, slices, x_le)
+        assert np.array_equal(T1, cpsd[t + "T_nvt"])                          # same weights, same summation order
+        assert np.array_equal(w1, cpsd[t + "nvt_eigval"])
+        f_n = O.smooth_normals(cpsd[t + "nvt_eigval"], cpsd[t + "nvt_eigvec"], cpsd[t + "n_in"])
+        assert angle_between(f_n, cpsd[t + "f_n"]).max() < 1e-4
+        w2, V2, C2, _ = O.pvt_normal_filtered(cpsd[t + "pos_in"], cpsd[t + "f_n"], np.arange(n), j, slices, x_le)
+        assert np.abs(C2 - cpsd[t + "T_pvt"]).max() <= 1e-6 * np.abs(cpsd[t + "T_pvt"]).max()
+        assert np.array_equal(O.vu_features(cpsd[t + "pvt_eigval"], 0.3), cpsd[t + "classes"])
+        assert (O.vu_features(w2, 0.3) == cpsd[t + "classes"]).mean() > 0.9995
+
+
+def test_cpsd_steps_on_ball_rows(cpsd):
+    n = len(cpsd["pos0"])
+    j, slices = cpsd["it0_ball_j"].astype(np.int64), cpsd["it0_ball_slices"]
+    pos, f_n, d = cpsd["it0_pos_in"], cpsd["it0_f_n"], cpsd["d"]
+    scale = np.abs(pos).max()
+    for key, name in enumerate(("flat", "edge", "corner", "feature")):
+        rows = np.nonzero(np.arange(n) % 4 == key)[0]
+        lens = np.diff(slices)[rows]
+        sub_slices = np.concatenate([[0], np.cumsum(lens)])
+        sub_j = np.concatenate([j[slices[r]:slices[r + 1]] for r in rows])
+        got = O.csr_step(name, pos, f_n, rows, sub_j, sub_slices, d, 0.5, edge_vec=cpsd["it0_pvt_eigvec"][:, :, 0])
+        err = np.abs(got - cpsd["ballrows_" + name]).max(axis=1) / scale
+        # near-singular systems on tiny balls (1-3 neighbours) amplify the solver's rounding; they are clamped by d
+        assert (err > 1e-5).mean() < 0.01, (name, (err > 1e-5).mean(), err.max())
+
+
+def test_cpsd_loop(cpsd):
+    pos, nrm = cpsd["pos0"], cpsd["n0"]
+    scale = np.abs(pos).max()
+    for it in range(2):
+        t = f"it{it}_"
+        # teacher-forced per iteration: the reference's inputs in, its outputs compared
+        new, f_n, lab, temp = O.cpsd_iteration(cpsd["pos0"], cpsd[t + "pos_in"], cpsd[t + "n_in"], cpsd["pos0"], cpsd["d"])
+        assert (lab == cpsd[t + "classes"]).mean() > 0.999
+        assert (angle_between(f_n, cpsd[t + "f_n"]) > 1e-4).mean() < 0.002
+        same = lab == cpsd[t + "classes"]
+        err = np.abs(new - cpsd[t + "pos_out"]).max(axis=1) / scale
+        assert (err[same] > 1e-5).mean() < 0.01, (err[same] > 1e-5).mean()
