@@ -299,6 +299,38 @@ def run_ours(args):
         e2e = {"value": n * e_steps / float(t.item()), "unit": "point-iterations/s", "h2d_bytes_per_step": n * 24, "d2h_bytes_per_step": n * 25,
                "steps": e_steps, "call": "SlabSession.step_host (each rank: pinned host buffers of its slab in and out, halo exchange over NCCL)"}
 
+    # ---- the metric's second half: kNN queries/s through the public ngpd_knn (no temporal coherence: every query searched)
+    knn_line = None
+    if world == 1 and not args.no_knn:
+        del sess
+        profile_src = None
+        torch.cuda.empty_cache()
+        grid = _lib.Grid(noisy, K_F)
+        flags = _lib.KNN_QUERY_IS_TREE
+        for _ in range(2):
+            tab = grid.knn(noisy, K_F, flags)
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        k0.record()
+        for _ in range(3):
+            tab = grid.knn(noisy, K_F, flags)
+        k1.record()
+        torch.cuda.synchronize()
+        kms = k0.elapsed_time(k1) / 3
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d2 = grid.nn_sqdist(noisy, False, flags)
+        c0.record()
+        for _ in range(3):
+            d2 = grid.nn_sqdist(noisy, False, flags)
+        c1.record()
+        torch.cuda.synchronize()
+        cms = c0.elapsed_time(c1) / 3
+        knn_line = {"metric": "kNN queries/sec", "k": K_F, "value": n / (kms * 1e-3), "ms": kms, "algorithmic_bytes_per_query": 24 + 4 * K_F,
+                    "frac_of_hbm_peak": (24 + 4 * K_F) * n / (kms * 1e-3) / 1e9 / peak,
+                    "nearest_neighbour_queries_per_s": n / (cms * 1e-3), "nearest_ms": cms,
+                    "call": "ngpd_knn / ngpd_nn_sqdist (public ABI, queries = the tree's own noisy points, index output materialised)"}
+        del tab, d2, grid
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -330,7 +362,7 @@ def run_ours(args):
     line = {"metric": "denoise point-iterations/sec (kNN+NVT+update)", "value": value, "unit": "point-iterations/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, n), "clocks": clocks,
-            "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu}
+            "e2e": e2e, "knn": knn_line, "gpu_launches": launches, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -345,6 +377,7 @@ def main():
     ap.add_argument("--cpu-points", type=int, default=200_000)
     ap.add_argument("--ref-points", type=int, default=400_000)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-knn", action="store_true")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -449,7 +449,9 @@ extern "C" __attribute__((visibility("default"))) int ngpd_grid_create(const flo
     double ex = (double)G->bbox[3] - G->bbox[0], ey = (double)G->bbox[4] - G->bbox[1], ez = (double)G->bbox[5] - G->bbox[2];
     double emax = std::max(ex, std::max(ey, ez));
     if (emax <= 0) emax = 1.0;
-    const double target = std::max(2.0, 0.40 * (double)(k_hint > 0 ? k_hint : 16));   // points per occupied cell
+    // points per occupied cell: 0.4 k, but no more than for k = 32 -- longer rows of cells would not fit the streaming
+    // search's 64-point range slots, and a k = 64 query is answered by the 5x5x5 tier anyway
+    const double target = std::max(2.0, 0.40 * (double)std::min(k_hint > 0 ? k_hint : 16, 32));
     double h;
     bool fixed = cell_size > 0.0f;
     if (fixed) {

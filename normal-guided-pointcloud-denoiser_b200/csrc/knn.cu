@@ -197,7 +197,7 @@ extern "C" __attribute__((visibility("default"))) int ngpd_knn(const ngpd_grid_t
     else if (k <= 8) { if (exact_only) launch_knn<8>(G, query, order, m, k, skip, idx_out, d2_out, stream); else rc = launch_knn_fast<8>(G, query, order, m, k, skip, idx_out, d2_out, stream); }
     else if (k <= 16) { if (exact_only) launch_knn<16>(G, query, order, m, k, skip, idx_out, d2_out, stream); else rc = launch_knn_fast<16>(G, query, order, m, k, skip, idx_out, d2_out, stream); }
     else if (k <= 32) { if (exact_only) launch_knn<32>(G, query, order, m, k, skip, idx_out, d2_out, stream); else rc = launch_knn_fast<32>(G, query, order, m, k, skip, idx_out, d2_out, stream); }
-    else launch_knn<64>(G, query, order, m, k, skip, idx_out, d2_out, stream);
+    else { if (exact_only) launch_knn<64>(G, query, order, m, k, skip, idx_out, d2_out, stream); else rc = launch_knn_fast<64>(G, query, order, m, k, skip, idx_out, d2_out, stream); }
     if (rc) return rc;
     NGPD_CUDA_OK(cudaGetLastError());
     if (order) NGPD_CUDA_OK(cudaFreeAsync(order, stream));

@@ -124,7 +124,7 @@ __device__ __forceinline__ void session_write_row(int64_t s, int k, const int (&
 
 // tier 0: every row whose stored candidates still answer the query; the others are listed for the search tiers
 template <int K>
-__global__ void __launch_bounds__(128, 4) session_knn_rerank_kernel(GridView g, const float4* __restrict__ pos, const uint8_t* __restrict__ owned,
+__global__ void __launch_bounds__(128, 5) session_knn_rerank_kernel(GridView g, const float4* __restrict__ pos, const uint8_t* __restrict__ owned,
                                                                  int64_t n, int k, int32_t* __restrict__ idx, KnnTrack tr,
                                                                  int32_t* __restrict__ fail_list, int32_t* __restrict__ fail_count) {
     __shared__ KsCandTile<2 * K> tile;
@@ -484,7 +484,7 @@ __device__ __forceinline__ V3 session_move_point(int kind, const Quad4& pos, con
 
 // one class: members move, everybody else is copied through to the other buffer (snapshot semantics)
 template <int KU>
-__global__ void __launch_bounds__(128) session_update_kernel(int kind, int key, Quad4 pos, Quad4 fn, const float4* __restrict__ edge,
+__global__ void __launch_bounds__(128, 10) session_update_kernel(int kind, int key, Quad4 pos, Quad4 fn, const float4* __restrict__ edge,
                                                              const uint8_t* __restrict__ label, const uint8_t* __restrict__ owned,
                                                              const int32_t* __restrict__ idx, int64_t n, int k, int ku, float alpha, float dmax,
                                                              const float* __restrict__ cd, float4* __restrict__ out) {
@@ -673,7 +673,7 @@ static int run_knn(ngpd_session* S, int k, int32_t* idx, cudaStream_t st, bool t
     unsigned b = (unsigned)cdiv(S->n, 128);
     const GridView& g = S->grid->v;
     const float4* p = S->pos[S->cur];
-    const bool fast = !S->exact_only && k > 4 && k <= 32;
+    const bool fast = !S->exact_only && k > 4 && k <= 64;
     int rc = 0;
     S->knn_launches = 1;
     if (fast) {
@@ -681,7 +681,8 @@ static int run_knn(ngpd_session* S, int k, int32_t* idx, cudaStream_t st, bool t
         const int kt = (S->use_rerank && S->cand_k >= k && !track) ? S->cand_k : k;
         if (kt <= 8) rc = run_knn_fast<8>(S, k, idx, st, track);
         else if (kt <= 16) rc = run_knn_fast<16>(S, k, idx, st, track);
-        else rc = run_knn_fast<32>(S, k, idx, st, track);
+        else if (kt <= 32) rc = run_knn_fast<32>(S, k, idx, st, track);
+        else rc = run_knn_fast<64>(S, k, idx, st, track);
     }
     else if (k <= 4) session_knn_kernel<4><<<b, 128, 0, st>>>(g, p, S->owned, S->n, k, idx);
     else if (k <= 8) session_knn_kernel<8><<<b, 128, 0, st>>>(g, p, S->owned, S->n, k, idx);

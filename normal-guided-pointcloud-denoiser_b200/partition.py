@@ -126,18 +126,14 @@ class HaloExchanger:
                 w.wait()
 
     def exchange(self, send_buf: torch.Tensor, recv_buf: torch.Tensor):
-        """send_buf rows are ordered by peer as in send_local (concatenated), recv_buf likewise for recv_local."""
-        rank = self.plan.rank
-        sends, recvs, so, ro = [], [], 0, 0
-        for q in range(self.plan.world):
-            sc, rc = self.send_counts[q], self.recv_counts[q]
-            if q != rank and sc:
-                sends.append((send_buf[so:so + sc], q))
-            if q != rank and rc:
-                recvs.append((recv_buf[ro:ro + rc], q))
-            so += sc
-            ro += rc
-        self._p2p(sends, recvs)
+        """send_buf rows are ordered by peer as in send_local (concatenated), recv_buf likewise for recv_local.
+        One variable-split all-to-all per exchange: a single collective call (one NCCL kernel) instead of up to
+        2*(world-1) point-to-point operations -- at 8 GPUs the host-side cost of building and launching those was larger
+        than the iteration's kernels (measured: 3.7 ms of a 7.7 ms step)."""
+        if self.plan.world == 1:
+            return
+        dist.all_to_all_single(recv_buf, send_buf, output_split_sizes=self.recv_counts, input_split_sizes=self.send_counts,
+                               group=self.group)
 
     def bytes_per_exchange(self, row_bytes: int = 16):
         return sum(self.send_counts) * row_bytes, sum(self.recv_counts) * row_bytes
@@ -226,6 +222,12 @@ class SlabSession:
         ptr = self._lib.load().ngpd_session_buffer(self.session._h, which)
         return torch.as_tensor(_DevView(ptr, shape, typestr), device=self._send_buf.device)
 
+    def _views(self):
+        # the flat-step accumulators live at fixed addresses for the session's life: wrap them once
+        if not hasattr(self, "_scalar_views"):
+            self._scalar_views = (self._scalar_view(3, (4,), "<f8"), self._scalar_view(4, (4,), "<f4")[3:4])
+        return self._scalar_views
+
     def step(self):
         import ctypes
         lib, L, p = self._lib.load(), self._lib, self.params
@@ -242,10 +244,10 @@ class SlabSession:
             if kind == L.STEP_FLAT:
                 L.check(lib.ngpd_session_phase_flat_scalars(h, ref, key, 0, st()), "flat scalars 0")
                 if self.world > 1:
-                    dist.all_reduce(self._scalar_view(3, (4,), "<f8"), group=self.group)
+                    dist.all_reduce(self._views()[0], group=self.group)
                 L.check(lib.ngpd_session_phase_flat_scalars(h, ref, key, 1, st()), "flat scalars 1")
                 if self.world > 1:
-                    dist.all_reduce(self._scalar_view(4, (4,), "<f4")[3:4], op=dist.ReduceOp.MAX, group=self.group)
+                    dist.all_reduce(self._views()[1], op=dist.ReduceOp.MAX, group=self.group)
             L.check(lib.ngpd_session_phase_update(h, ref, key, st()), "phase_update")
             self._refresh(0)                                    # the class' new positions, before the next class reads them
         L.check(lib.ngpd_session_phase_commit_normals(h), "commit normals")

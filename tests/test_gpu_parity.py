@@ -108,7 +108,7 @@ def test_knn_random_clouds_bit_exact(ng, kind, k):
     assert np.array_equal(d2.cpu().numpy(), ref_d2)
 
 
-@pytest.mark.parametrize("k", [8, 16, 32])
+@pytest.mark.parametrize("k", [8, 16, 32, 64])
 def test_knn_fast_path_equals_exact_search(ng, k):
     """the warp-lockstep fast path (+ fix-up list) returns exactly the rows of the exact shell search"""
     n = 600_000
