@@ -132,6 +132,14 @@ int ngpd_update(int kind, const float* pos, const float* nrm, const float* edge_
 /* sum of |pos[idx] - pos[row]| over all edges (TorchUtils.averageEdgeLength, Utils.py:298): out2 = {sum, count} fp64 */
 int ngpd_edge_length_sum(const float* pos, const int32_t* idx, const int32_t* rows, int64_t m, int k, double* out2, void* stream);
 
+/* ---- mesh vertex update: PatchGeneration.Modules.Mesh.updateVertices(n, k), Mesh.py:377-418 (the Vertex_updating
+ * notebook's algorithm).  fp64.  v [nv,3], faces [nf,3] int32, face_normals [nf,3] (the target normals),
+ * vertex-triangle adjacency as igl.vertex_triangle_adjacency returns it: vta_faces [sum deg] + vta_offsets [nv+1].
+ * `iterations` Jacobi sweeps; v_out must not alias v; scratch (nv*3 doubles) is needed for more than one sweep. */
+int ngpd_mesh_vertex_update(const double* v, int64_t nv, const int32_t* faces, const double* face_normals,
+                            const int32_t* vta_faces, const int32_t* vta_offsets, int iterations,
+                            double* scratch /*nullable*/, double* v_out, void* stream);
+
 /* ---- fused session: Processor.denoise / denoiseUntilMinimumError bodies (Processor.py:124-139,158-176)
  * on tree-ordered float4 state.  The index is frozen on `tree_pos` (what Processor.__init__ saw); pos/nrm are
  * the current state in ORIGINAL point order. */

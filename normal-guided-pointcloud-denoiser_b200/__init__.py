@@ -5,6 +5,7 @@ from . import _lib  # noqa: F401
 from .Decompositionor import Decomposition, Decompositionor  # noqa: F401
 from .Denoiser import Denoiser  # noqa: F401
 from .GraphBuilder import Graph, GraphBuilder  # noqa: F401
+from .Mesh import Mesh  # noqa: F401
 from .Noise import Noise  # noqa: F401
 from .Object import Pointcloud  # noqa: F401
 from .Processor import Processor  # noqa: F401

@@ -40,6 +40,7 @@ SIGNATURES = {
     "ngpd_ball_query": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, ctypes.c_int, c_vp, c_vp, c_vp, c_vp]),
     "ngpd_nvt_normal": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.c_int, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ngpd_pvt_normal": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.c_int, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "ngpd_mesh_vertex_update": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, ctypes.c_int, c_vp, c_vp, c_vp]),
     "ngpd_pca_normals": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, ctypes.c_int, c_vp, c_vp, c_vp, c_vp]),
     "ngpd_nvt": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.c_int, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ngpd_eigh3": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),

@@ -664,3 +664,30 @@ def cpsd_iteration(tree, pos, nrm, original_pos, d, rho=0.9, tau=0.3, alphas=(0.
     new = pos.copy()
     new[mask] = temp[mask]
     return new, f_n, lab, temp
+
+
+# ------------------------------------------------------------------------------------------------
+# mesh vertex update (PatchGeneration.Modules.Mesh.updateVertices, Mesh.py:377-418)
+# ------------------------------------------------------------------------------------------------
+def mesh_vertex_update(v, f, face_normals, vta_faces, vta_offsets, k=15):
+    """k Jacobi sweeps of  v_i += 1/(3 deg_i) sum_{f at i} sum_{c in f} n_f (n_f . (v_c - v_i)), fp64, every vertex from
+    the same snapshot.  Sums run over the incident faces first (per corner), then over the three corners, as the
+    reference's two np.sum calls do."""
+    v = np.array(v, dtype=np.float64)
+    f = np.asarray(f, dtype=np.int64)
+    n = np.asarray(face_normals, dtype=np.float64)
+    vf = np.asarray(vta_faces, dtype=np.int64)
+    ni = np.asarray(vta_offsets, dtype=np.int64)
+    deg = np.diff(ni)
+    owner = np.repeat(np.arange(len(v)), deg)
+    for _ in range(k):
+        nj = n[vf]                                        # [E,3]
+        dvs = v[f[vf]] - v[owner][:, None, :]             # [E,3 corners,3]
+        dot = ((nj[:, None, 0] * dvs[:, :, 0] + nj[:, None, 1] * dvs[:, :, 1]) + nj[:, None, 2] * dvs[:, :, 2])
+        el = dot[:, :, None] * nj[:, None, :]             # [E,corner,axis]
+        S = np.zeros((len(v), 3, 3))
+        np.add.at(S, owner, el)                           # sequential over the incident faces, in adjacency order
+        S = (S[:, 0] + S[:, 1]) + S[:, 2]
+        with np.errstate(invalid="ignore", divide="ignore"):
+            v = v + S / (3 * deg)[:, None]
+    return v

@@ -1,0 +1,63 @@
+"""BASELINE.json configs[0] and configs[1] through the mirror of the reference API, on the clouds recorded in tests/golden/
+(the GPU box has no /root/reference): wall time of Processor.denoise() and of denoiseUntilMinimumError incl. the Chamfer
+evaluation each iteration, next to the reference's own time for the same call (measured at survey
+time in the build container).  Markdown on stdout."""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+import ngpd_b200 as ng
+
+G = os.path.join(ROOT, "tests", "golden")
+cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def wall(fn, reps):
+    fn(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        out = fn()
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / reps, out
+
+
+print("| config | cloud | points | call | ours ms | iterations | point-iterations/s | CD before -> after | reference (CPU, survey) |")
+print("|---|---|---|---|---|---|---|---|---|")
+f = dict(np.load(os.path.join(G, "fandisk_denoise.npz")))
+n = len(f["pos0"])
+
+
+def config1():
+    p = ng.Processor(ng.Pointcloud(cu(f["pos0"]).clone()))
+    p.graph.n = cu(f["n_flip"]).clone()
+    p.denoise()
+    return p.graph.pos
+
+
+t, pos = wall(config1, 5)
+cd0 = float(ng.TorchUtils.ChamferDistance(cu(f["gt"]), cu(f["pos0"])).mean()); cd1 = float(ng.TorchUtils.ChamferDistance(cu(f["gt"]), pos).mean())
+print(f"| 0 | models/fandisk_gaus_n6_noisy.obj | {n} | Processor(pc) + denoise() (2 iterations, k=16/8) | {t * 1e3:.2f} | 2 | {2 * n / t:.3g} | {cd0:.4f} -> {cd1:.4f} | 1.77 s cold, CD 0.3853 -> 0.2264 |")
+
+u = dict(np.load(os.path.join(G, "until_min.npz")))
+n = len(u["pos0"])
+iters = {}
+
+
+def config2():
+    p = ng.Processor(ng.Pointcloud(cu(u["pos0"]).clone()))
+    p.graph.n = cu(u["n_flip"]).clone()
+    strategy = {0: p.denoiser.flat_step, 1: p.denoiser.feature_step, 2: p.denoiser.feature_step}
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        best, err, it = p.denoiseUntilMinimumError(cu(u["gt"]), strategy, k=8, alpha=[1, 0.2, 1], d=2 * float(u["l"]),
+                                                    error_funcs=[ng.TorchUtils.ChamferDistance])
+    iters["n"] = it
+    return best, err
+
+
+t, (best, err) = wall(config2, 5)
+it = iters["n"] + 1
+cd0 = float(ng.TorchUtils.ChamferDistance(cu(u["gt"]), cu(u["pos0"])).mean())
+print(f"| 1 | Generated_Noise/{str(u['cloud'])}.obj | {n} | Processor(pc) + denoiseUntilMinimumError (flat/feature/feature, k=8, CD each iteration) | {t * 1e3:.2f} | {it} | "
+      f"{it * n / t:.3g} | {cd0:.4e} -> {float(err[0].mean()):.4e} | {it} iterations, 35.3 k point-iterations/s excl. Chamfer, CD 1.7154e-7 -> 1.5591e-7 |")

@@ -54,9 +54,9 @@ void hm_weight(const float* vi, const float* vj, const float* nj, int64_t m, flo
     NvtThreshold th(x_thresh);
     for (int64_t r = 0; r < m; ++r) {
         exact[r] = nvt_weight(A(r), B(r), N(r), x_thresh);
-        bool certain = th.quick;
-        bool q = nvt_weight_quick(A(r), B(r), N(r), th, certain);
-        quick[r] = certain ? q : nvt_weight(A(r), B(r), N(r), x_thresh);
+        float slack = th.quick ? 1.0f : -1.0f;
+        bool q = nvt_weight_quick(A(r), B(r), N(r), th, slack);
+        quick[r] = slack > NGPD_NVT_SLACK_FLOOR ? q : nvt_weight(A(r), B(r), N(r), x_thresh);
     }
 }
 

@@ -811,3 +811,60 @@ def test_cpsd_loop_vs_reference(ng, cpsd):
         assert agree > (0.999 if it == 0 else 0.97)
         if it == 0:
             assert bad_n < 0.01 and (err > 1e-5).mean() < 0.02
+
+
+def test_tensor_division_is_correctly_rounded(ng):
+    """The voting tensor divides six sums by the vote count with one shared reciprocal + remainder correction
+    (point_math.cuh: CountDivider).  Every count 1..64 with random rows: bit-equal to IEEE division of the same sums."""
+    rng = np.random.default_rng(11)
+    n, reps = 4096, 64 * 200
+    nrm = rng.normal(size=(n, 3)); nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    nrm = nrm.astype(np.float32)
+    pos = rng.normal(size=(n, 3)).astype(np.float32)
+    lens = np.tile(np.arange(1, 65), reps // 64)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    j = rng.integers(0, n, off[-1]).astype(np.int32)
+    rows = rng.integers(0, n, len(lens)).astype(np.int32)
+    m = len(lens)
+    ev = torch.empty((m, 3), device="cuda"); vec = torch.empty((m, 3, 3), device="cuda"); T = torch.empty((m, 3, 3), device="cuda")
+    sw = torch.empty(m, dtype=torch.int32, device="cuda")
+    lib = ng._lib.load()
+    # x_thresh = 1: every neighbour votes (the quick test is off at the ends of the range, the exact sequence passes |x| <= 1)
+    ng._lib.check(lib.ngpd_nvt(cu(pos).data_ptr(), cu(nrm).data_ptr(), cu(j).data_ptr(), cu(off).data_ptr(), cu(rows).data_ptr(), m, 0,
+                               1.0, ev.data_ptr(), vec.data_ptr(), T.data_ptr(), sw.data_ptr(), None), "nvt")
+    assert np.array_equal(sw.cpu().numpy(), lens)
+    got = T.cpu().numpy()
+    for L in range(1, 65):
+        r = np.nonzero(lens == L)[0]
+        nj = nrm[j[off[r][:, None] + np.arange(L)[None, :]]]                      # [rows, L, 3]
+        outer = (nj[:, :, :, None] * nj[:, :, None, :]).astype(np.float32)
+        acc = np.zeros((len(r), 3, 3), np.float32)
+        for a in range(L):
+            acc = (acc + outer[:, a]).astype(np.float32)
+        want = (acc / np.float32(L)).astype(np.float32)
+        assert np.array_equal(got[r], want), L
+
+
+# ------------------------------------------------------------------------------------------------------
+# mesh vertex update (Vertex_updating notebook, SURVEY 8f rank 4)
+# ------------------------------------------------------------------------------------------------------
+def test_mesh_vertex_update(ng):
+    m = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "mesh_update.npz")))
+    scale = np.abs(m["v_noisy"]).max()
+    for k in (1, 5):
+        mesh = ng.Mesh(m["v_noisy"].copy(), m["f"])
+        assert np.array_equal(mesh.getVertexTriangleAdjacency()[0], m["vta_faces"]) and np.array_equal(mesh.getVertexTriangleAdjacency()[1], m["vta_offsets"])
+        mesh.updateVertices(m["face_normals"], k)
+        assert np.abs(mesh.getVertices() - m[f"v_after_{k}"]).max() <= 1e-12 * scale, k
+    # face normals as the reference computes them; the update pulls them towards the targets
+    mesh = ng.Mesh(m["v_noisy"].copy(), m["f"])
+    before = (mesh.getFaceNormals() * m["face_normals"]).sum(1).mean()
+    mesh.updateVertices(m["face_normals"], 15)
+    after = (mesh.getFaceNormals() * m["face_normals"]).sum(1).mean()
+    assert after > before and after > 0.97
+    # k = 0 leaves the vertices alone; a vertex without faces divides 0 by 0 like the reference (NaN), others are unaffected
+    mesh0 = ng.Mesh(m["v_noisy"].copy(), m["f"]); mesh0.updateVertices(m["face_normals"], 0)
+    assert np.array_equal(mesh0.getVertices(), m["v_noisy"])
+    v_extra = np.concatenate([m["v_noisy"], [[0.0, 0.0, 0.0]]])
+    mesh1 = ng.Mesh(v_extra, m["f"]); mesh1.updateVertices(m["face_normals"], 1)
+    assert np.isnan(mesh1.getVertices()[-1]).all() and np.abs(mesh1.getVertices()[:-1] - m["v_after_1"]).max() <= 1e-12 * scale

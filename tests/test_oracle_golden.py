@@ -207,3 +207,12 @@ def test_cpsd_loop(cpsd):
         same = lab == cpsd[t + "classes"]
         err = np.abs(new - cpsd[t + "pos_out"]).max(axis=1) / scale
         assert (err[same] > 1e-5).mean() < 0.01, (err[same] > 1e-5).mean()
+
+
+def test_mesh_vertex_update_vs_reference():
+    """PatchGeneration.Modules.Mesh.updateVertices (tests/golden/make_golden_mesh.py)"""
+    import os
+    m = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "mesh_update.npz")))
+    for k in (1, 5):
+        got = O.mesh_vertex_update(m["v_noisy"], m["f"], m["face_normals"], m["vta_faces"], m["vta_offsets"], k)
+        assert np.abs(got - m[f"v_after_{k}"]).max() <= 1e-12 * np.abs(m["v_noisy"]).max()
