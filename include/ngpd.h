@@ -132,6 +132,15 @@ int ngpd_update(int kind, const float* pos, const float* nrm, const float* edge_
 /* sum of |pos[idx] - pos[row]| over all edges (TorchUtils.averageEdgeLength, Utils.py:298): out2 = {sum, count} fp64 */
 int ngpd_edge_length_sum(const float* pos, const int32_t* idx, const int32_t* rows, int64_t m, int k, double* out2, void* stream);
 
+/* ---- consistent normal orientation: GraphBuilder.flipNormals, GraphBuilder.py:129-209.
+ * Edge cost 1 - |n_u . n_v| on the given graph (edges are taken as undirected; e directed entries), minimum spanning tree
+ * (ties ordered by (cost, lower endpoint, higher endpoint)), signs propagated from the top-most point (max z, made to point
+ * up): a child is flipped when n_parent . n_child < flip_threshold (the reference: cos(7 pi / 12)).  nrm is updated in
+ * place; components not connected to the root keep their normals, as in the reference.  Synchronises.
+ * info_out_host (nullable, 3 ints): connected components of the graph, breadth-first levels, Boruvka rounds. */
+int ngpd_orient_normals(const float* pos, float* nrm, int64_t n, const int32_t* edge_src, const int32_t* edge_dst, int64_t e,
+                        float flip_threshold, int32_t* info_out_host /*nullable*/, void* stream);
+
 /* ---- mesh vertex update: PatchGeneration.Modules.Mesh.updateVertices(n, k), Mesh.py:377-418 (the Vertex_updating
  * notebook's algorithm).  fp64.  v [nv,3], faces [nf,3] int32, face_normals [nf,3] (the target normals),
  * vertex-triangle adjacency as igl.vertex_triangle_adjacency returns it: vta_faces [sum deg] + vta_offsets [nv+1].

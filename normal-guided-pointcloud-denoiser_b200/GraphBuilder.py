@@ -88,9 +88,9 @@ class GraphBuilder:
         if flip:
             self.flipNormals()
 
-    # ---- orientation (:129-209).  Preprocessing, runs once; host-side for now (SURVEY.md 8f rank 2 is the
-    # GPU version): edge cost 1-|ni.nj|, minimum spanning tree, propagate from the top-most point flipping a
-    # child when n_parent.n_child < cos(7pi/12).
+    # ---- orientation (:129-209): edge cost 1-|ni.nj|, minimum spanning tree, propagate from the top-most point
+    # flipping a child when n_parent.n_child < cos(7pi/12).  On the GPU (Boruvka rounds + breadth-first frontier,
+    # csrc/orient.cu); flipNormalsHost is the SciPy version of the same definition, kept for cross-checks.
     def calculateEdgeCost(self) -> None:
         g = self.graph
         GeneralUtils.validateAttributes(g, ["edge_index", "n"])
@@ -98,6 +98,21 @@ class GraphBuilder:
         g.edge_attr = 1 - (nn[0] * nn[1]).sum(dim=-1).abs_()
 
     def flipNormals(self) -> None:
+        import ctypes
+        g = self.graph
+        GeneralUtils.validateAttributes(g, ["pos", "edge_index", "n"])
+        self.calculateEdgeCost()                       # the reference leaves graph.edge_attr behind (:131)
+        pos = _lib.dev(g.pos, torch.float32, "graph.pos")
+        nrm = _lib.dev(g.n, torch.float32, "graph.n").clone()
+        src = g.edge_index[0].to(torch.int32).contiguous()
+        dst = g.edge_index[1].to(torch.int32).contiguous()
+        info = (ctypes.c_int32 * 3)()
+        _lib.check(_lib.load().ngpd_orient_normals(_lib.ptr(pos), _lib.ptr(nrm), pos.size(0), _lib.ptr(src), _lib.ptr(dst), src.numel(),
+                                                   math.cos(7.0 / 12.0 * math.pi), info, _lib.stream()), "ngpd_orient_normals")
+        self.orientation_info = {"components": info[0], "levels": info[1], "rounds": info[2]}
+        g.n = nrm
+
+    def flipNormalsHost(self) -> None:
         from scipy.sparse import coo_matrix
         from scipy.sparse.csgraph import breadth_first_order, minimum_spanning_tree
 

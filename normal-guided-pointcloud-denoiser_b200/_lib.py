@@ -41,6 +41,7 @@ SIGNATURES = {
     "ngpd_nvt_normal": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.c_int, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ngpd_pvt_normal": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.c_int, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ngpd_mesh_vertex_update": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, ctypes.c_int, c_vp, c_vp, c_vp]),
+    "ngpd_orient_normals": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_f32, ctypes.POINTER(c_i32), c_vp]),
     "ngpd_pca_normals": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, ctypes.c_int, c_vp, c_vp, c_vp, c_vp]),
     "ngpd_nvt": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.c_int, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ngpd_eigh3": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libngpd.so")
-SOURCES = ["grid.cu", "knn.cu", "ball.cu", "nbr.cu", "mesh.cu", "session.cu"]
+SOURCES = ["grid.cu", "knn.cu", "ball.cu", "nbr.cu", "mesh.cu", "orient.cu", "session.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--fmad=false", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--threads", "4"]
 

@@ -830,8 +830,10 @@ def test_tensor_division_is_correctly_rounded(ng):
     sw = torch.empty(m, dtype=torch.int32, device="cuda")
     lib = ng._lib.load()
     # x_thresh = 1: every neighbour votes (the quick test is off at the ends of the range, the exact sequence passes |x| <= 1)
-    ng._lib.check(lib.ngpd_nvt(cu(pos).data_ptr(), cu(nrm).data_ptr(), cu(j).data_ptr(), cu(off).data_ptr(), cu(rows).data_ptr(), m, 0,
+    d_pos, d_nrm, d_j, d_off, d_rows = cu(pos), cu(nrm), cu(j), cu(off), cu(rows)          # keep the device copies alive
+    ng._lib.check(lib.ngpd_nvt(d_pos.data_ptr(), d_nrm.data_ptr(), d_j.data_ptr(), d_off.data_ptr(), d_rows.data_ptr(), m, 0,
                                1.0, ev.data_ptr(), vec.data_ptr(), T.data_ptr(), sw.data_ptr(), None), "nvt")
+    torch.cuda.synchronize()
     assert np.array_equal(sw.cpu().numpy(), lens)
     got = T.cpu().numpy()
     for L in range(1, 65):
@@ -868,3 +870,72 @@ def test_mesh_vertex_update(ng):
     v_extra = np.concatenate([m["v_noisy"], [[0.0, 0.0, 0.0]]])
     mesh1 = ng.Mesh(v_extra, m["f"]); mesh1.updateVertices(m["face_normals"], 1)
     assert np.isnan(mesh1.getVertices()[-1]).all() and np.abs(mesh1.getVertices()[:-1] - m["v_after_1"]).max() <= 1e-12 * scale
+
+
+# ------------------------------------------------------------------------------------------------------
+# normal orientation on the GPU (GraphBuilder.flipNormals)
+# ------------------------------------------------------------------------------------------------------
+def _knn_graph(ng, pos, k):
+    p = ng.Processor(ng.Pointcloud(cu(pos).clone()))
+    p.graph.edge_index = p.graphBuilder.getKNNEdgeIndex(k)
+    return p
+
+
+def test_orientation_vs_reference(ng, fandisk):
+    p = _knn_graph(ng, fandisk["pos0"], 12)
+    assert np.array_equal(p.graph.edge_index[1].view(-1, 12).cpu().numpy(), fandisk["knn12_noself"])
+    p.graph.n = cu(fandisk["n_pca"]).clone()
+    p.graphBuilder.flipNormals()
+    n_gpu = p.graph.n.cpu().numpy()
+    assert np.array_equal(np.abs(n_gpu), np.abs(fandisk["n_pca"]))                    # only signs change
+    agree = ((n_gpu * fandisk["n_flip"]).sum(1) > 0).mean()
+    # the reference's unstable argsort picks one of many minimum trees (flat regions: thousands of edges of cost exactly 0);
+    # the oracle's stable Kruskal agrees with it on 97-98 % of the signs, so does this tree
+    print(f"\norientation agrees with the reference on {agree:.4%} of the points; {p.graphBuilder.orientation_info}")
+    assert agree > 0.97
+    assert p.graphBuilder.orientation_info["components"] == 1
+    # the SciPy version of the same definition (another tie order)
+    q = _knn_graph(ng, fandisk["pos0"], 12)
+    q.graph.n = cu(fandisk["n_pca"]).clone()
+    q.graphBuilder.flipNormalsHost()
+    assert ((n_gpu * q.graph.n.cpu().numpy()).sum(1) > 0).mean() > 0.97
+
+
+def test_orientation_unique_tree_equals_oracle(ng):
+    """Random normals make all edge costs distinct: the minimum spanning tree is unique and the propagated signs must be
+    exactly those of the oracle's Kruskal + traversal."""
+    rng = np.random.default_rng(8)
+    pos = surface_cloud(8000, 8, noise=0.002)
+    nrm = rng.normal(size=pos.shape); nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    nrm = nrm.astype(np.float32)
+    p = _knn_graph(ng, pos, 10)
+    nbr = p.graph.edge_index[1].view(-1, 10).cpu().numpy()
+    p.graph.n = cu(nrm).clone()
+    p.graphBuilder.flipNormals()
+    want = O.orient_normals(pos, nrm, nbr)
+    assert np.array_equal(p.graph.n.cpu().numpy(), want)
+    assert p.graphBuilder.orientation_info["rounds"] <= 16
+
+
+def test_orientation_properties(ng):
+    """Two spheres far apart, normals radial with random signs: the sphere holding the top-most point comes out pointing
+    outwards everywhere, the other one (not connected to the root) is left alone -- as the reference's DFS does."""
+    rng = np.random.default_rng(9)
+    u = rng.normal(size=(30000, 3)); u /= np.linalg.norm(u, axis=1, keepdims=True)
+    top, low = u[:20000], u[20000:] * 0.5 + np.array([0.0, 0.0, -10.0])
+    pos = np.concatenate([top, low]).astype(np.float32)
+    radial = np.concatenate([u[:20000], u[20000:]]).astype(np.float32)
+    sign = rng.choice([-1.0, 1.0], len(pos)).astype(np.float32)
+    nrm = radial * sign[:, None]
+    p = _knn_graph(ng, pos, 8)
+    p.graph.n = cu(nrm).clone()
+    p.graphBuilder.flipNormals()
+    out = p.graph.n.cpu().numpy()
+    assert ((out[:20000] * radial[:20000]).sum(1) > 0).all()
+    assert np.array_equal(out[20000:], nrm[20000:])
+    assert p.graphBuilder.orientation_info["components"] >= 2
+    # deterministic
+    q = _knn_graph(ng, pos, 8)
+    q.graph.n = cu(nrm).clone()
+    q.graphBuilder.flipNormals()
+    assert torch.equal(p.graph.n, q.graph.n)
