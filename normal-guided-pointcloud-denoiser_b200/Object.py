@@ -34,6 +34,27 @@ def read_obj(file_path: str):
     return arr(v, np.float64), arr(vn, np.float64), arr(fv, np.int64), arr(fn, np.int64)
 
 
+def sample_points(pos: torch.Tensor, face: torch.Tensor, num: int):
+    """torch_geometric.transforms.SamplePoints(num, include_normals=True) on (pos [V,3], face [3,F]): (points, normals)."""
+    pos_max = pos.abs().max()
+    pos = pos / pos_max
+    v0, v1, v2 = pos[face[0]], pos[face[1]], pos[face[2]]
+    area = torch.linalg.cross(v1 - v0, v2 - v0, dim=1).norm(p=2, dim=1).abs() / 2
+    prob = area / area.sum()
+    sample = torch.multinomial(prob, num, replacement=True)
+    face = face[:, sample]
+    frac = torch.rand(num, 2, device=pos.device)
+    mask = frac.sum(dim=-1) > 1
+    frac[mask] = 1 - frac[mask]
+    vec1 = pos[face[1]] - pos[face[0]]
+    vec2 = pos[face[2]] - pos[face[0]]
+    normal = torch.nn.functional.normalize(torch.linalg.cross(vec1, vec2, dim=1), p=2)
+    pos_sampled = pos[face[0]]
+    pos_sampled = pos_sampled + frac[:, :1] * vec1
+    pos_sampled = pos_sampled + frac[:, 1:] * vec2
+    return pos_sampled * pos_max, normal
+
+
 class Pointcloud:
     def __init__(self, v: torch.Tensor, n: torch.Tensor = None) -> None:
         assert v.is_floating_point()
@@ -84,6 +105,26 @@ class Pointcloud:
             pc = cls(vt, torch.tensor(vn, dtype=torch.float, device=device))
         else:
             pc = cls(vt)
+        pc.file_path = file_path
+        return pc
+
+    @classmethod
+    def sampleObj(cls, file_path: str, num_points: int, device=None) -> "Pointcloud":
+        """Object.py:135-156: load an OBJ mesh and sample `num_points` points from its surface with their face normals.
+        The reference delegates to torch_geometric.transforms.SamplePoints(num, include_normals=True); its published
+        algorithm is restated here with torch ops on `device`: faces drawn with probability
+        proportional to area (multinomial with replacement, on coordinates normalised by max |pos|), a uniform point in
+        each by two folded barycentric fractions, the face's unit normal."""
+        path = Path(file_path)
+        assert path.is_file()
+        assert path.suffix == ".obj"
+        device = device if device is not None else _default_device()
+        v, _, fv, _ = read_obj(file_path)
+        pos = torch.tensor(v, dtype=torch.float, device=device)
+        face = torch.tensor(fv, dtype=torch.long, device=device).T
+        assert pos.size(1) == 3
+        assert face.size(0) == 3
+        pc = cls(*sample_points(pos, face, int(num_points)))
         pc.file_path = file_path
         return pc
 

@@ -116,3 +116,31 @@ def test_acos_threshold_matches_oracle():
     from ngpd_b200 import _lib
     for rho in (math.pi * 5 / 12, 0.9, 0.95, math.pi * 23 / 48):
         assert np.float32(_lib.acos_threshold(rho)) == O.acos_threshold(rho)
+
+
+def test_sample_obj_properties(tmp_path):
+    """Pointcloud.sampleObj (Object.py:135-156; torch_geometric's SamplePoints restated): points lie on the mesh, faces are
+    drawn in proportion to their area, normals are the faces' unit normals, the global torch seed makes it reproducible."""
+    import numpy as np
+    import torch
+    import ngpd_b200 as ng
+    # a unit square in z = 0 (two triangles) and a 2 x 2 square in x = 3 (two triangles): area ratio 1 : 4
+    obj = tmp_path / "two_squares.obj"
+    obj.write_text("\n".join(["v 0 0 0", "v 1 0 0", "v 1 1 0", "v 0 1 0", "v 3 0 0", "v 3 2 0", "v 3 2 2", "v 3 0 2",
+                               "f 1 2 3", "f 1 3 4", "f 5 6 7", "f 5 7 8"]) + "\n")
+    torch.manual_seed(0)
+    pc = ng.Pointcloud.sampleObj(str(obj), 20000, device="cpu")
+    v, n = pc.v.numpy(), pc.n.numpy()
+    assert v.shape == (20000, 3) and n.shape == (20000, 3) and pc.hasNormals()
+    small = np.abs(v[:, 2]) < 1e-6
+    big = np.abs(v[:, 0] - 3) < 1e-6
+    assert (small | big).all()
+    assert (v[small, :2] >= -1e-6).all() and (v[small, :2] <= 1 + 1e-6).all()
+    assert (v[big, 1:] >= -1e-6).all() and (v[big, 1:] <= 2 + 1e-6).all()
+    assert abs(big.mean() - 0.8) < 0.02                                          # area 4 of 5
+    assert np.allclose(np.abs(n[small]), [0, 0, 1], atol=1e-6) and np.allclose(np.abs(n[big]), [1, 0, 0], atol=1e-6)
+    # uniform inside a face: the mean of the small square's samples is its centre
+    assert np.abs(v[small, :2].mean(0) - 0.5).max() < 0.02
+    torch.manual_seed(0)
+    again = ng.Pointcloud.sampleObj(str(obj), 20000, device="cpu")
+    assert torch.equal(again.v, pc.v) and torch.equal(again.n, pc.n)
