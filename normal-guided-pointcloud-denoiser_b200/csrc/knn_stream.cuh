@@ -309,6 +309,14 @@ struct KsRowShared {
     __device__ __forceinline__ int operator()(int a) const { return tile.v[a][col]; }
 };
 
+// Keys of the re-ranking tier: a candidate is one of at most 64 slots of the row, so only 6 id bits are needed and the
+// distance field keeps all 23 mantissa bits of y = d2/h^2 + 32: its unit is 2^-18 h^2 instead of the 2^-16 of the streaming
+// tiers.  Error budget per key: 0.5 unit (rounding of y) + 0.15 (fp32 evaluation of d2) -> two candidates whose fields differ
+// by more than KS_RR_MARGIN units are in their exact order.
+constexpr int KS_RR_SHIFT = 9;
+constexpr unsigned KS_RR_IDMASK = (1u << KS_RR_SHIFT) - 1u;
+constexpr unsigned KS_RR_MARGIN = 3;
+
 template <int K, class Ids>
 __device__ __forceinline__ void ks_rerank_keys(const Ids& ids, int first, const float4* __restrict__ pts,
                                                float qx, float qy, float qz, float inv_h2, unsigned (&out)[K]) {
@@ -318,16 +326,16 @@ __device__ __forceinline__ void ks_rerank_keys(const Ids& ids, int first, const 
         const float4 p = __ldg(pts + max(j, 0));
         const float dx = p.x - qx, dy = p.y - qy, dz = p.z - qz;
         const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-        out[a] = j >= 0 ? (ks_dist_field<1>(d2, inv_h2) | (unsigned)(first + a)) : KS_NONE;
+        const float y = fminf(fmaf(d2, inv_h2, 32.0f), 63.99999f);      // NaN and far-away candidates saturate
+        out[a] = j >= 0 ? ((__float_as_uint(y) << KS_RR_SHIFT) | (unsigned)(first + a)) : KS_NONE;
     }
 }
 
 template <int K, class Ids>
 __device__ __forceinline__ bool ks_rerank(KsTop<ks_kf(K, 2 * K)>& t, const GridView& g, const Ids& ids, float4 anchor,
                                           float qx, float qy, float qz, double (&ex)[ks_kf(K, 2 * K)]) {
-    using C = KsCfg<1>;
     constexpr int KF = ks_kf(K, 2 * K);
-    static_assert(K % 4 == 0 && 2 * K <= (1 << C::IDBITS) && KF < 2 * K, "candidate slots must fit the key's id field");
+    static_assert(K % 4 == 0 && 2 * K <= (1 << KS_RR_SHIFT) && KF < 2 * K, "candidate slots must fit the key's id field");
     const float inv_h2 = (float)(g.inv_h * g.inv_h);
     unsigned lo[K], hi[K];
     ks_rerank_keys<K>(ids, 0, g.pts, qx, qy, qz, inv_h2, lo);
@@ -340,19 +348,36 @@ __device__ __forceinline__ bool ks_rerank(KsTop<ks_kf(K, 2 * K)>& t, const GridV
     for (int i = 0; i < K; ++i) ks_ce(lo[i], hi[i]);              // ascending against descending: two bitonic halves
     ks_bitonic_merge<K>(lo);
     ks_bitonic_merge<K>(hi);                                        // lo, hi = the 2K keys in ascending order
+    // Are the first K places decided by the keys alone?  Only if every neighbouring pair up to (K, K+1) differs by more than
+    // the margin; otherwise (1-2 % of the lanes at this resolution; exact duplicates always) the first KF candidates are
+    // re-evaluated in fp64 and ordered by (distance, original index) as in the search tiers.
+    bool tight = false;
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+        const unsigned x = lo[a] >> KS_RR_SHIFT, y = (a + 1 < K ? lo[a + 1 < K ? a + 1 : 0] : hi[0]) >> KS_RR_SHIFT;
+        tight = tight || y <= x + KS_RR_MARGIN;
+    }
 #pragma unroll
     for (int a = 0; a < KF; ++a) {
         const unsigned key = a < K ? lo[a < K ? a : 0] : hi[a >= K ? a - K : 0];
         t.key[a] = key;
-        t.id[a] = key != KS_NONE ? ids((int)(key & C::IDMASK)) : -1;
+        t.id[a] = key != KS_NONE ? ids((int)(key & KS_RR_IDMASK)) : -1;
     }
     const unsigned worst = lo[K - 1], next = hi[KF - K];
-    ks_finalize<KF, KF>(t, g.pts, qx, qy, qz, ex);
+    if (__any_sync(FULL, tight)) {
+        ks_finalize<KF, KF>(t, g.pts, qx, qy, qz, ex);            // (lanes whose order was already decided pass through unchanged)
+    } else {
+        // only the K-th distance is needed, for the certificate below
+        const int j = t.id[K - 1];
+        const float4 p = __ldg(g.pts + max(j, 0));
+        const double dx = (double)qx - (double)p.x, dy = (double)qy - (double)p.y, dz = (double)qz - (double)p.z;
+        ex[K - 1] = j >= 0 ? __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)) : DBL_MAX;
+    }
     // distance travelled since the anchor, rounded up
     const float ax = qx - anchor.x, ay = qy - anchor.y, az = qz - anchor.z;
     const float delta = sqrtf(fmaf(az, az, fmaf(ay, ay, ax * ax))) * 1.000001f;
     const bool full = worst != KS_NONE;
-    const bool clear = (next >> C::IDBITS) > (worst >> C::IDBITS) + 3u;
+    const bool clear = (next >> KS_RR_SHIFT) > (worst >> KS_RR_SHIFT) + KS_RR_MARGIN;
     const bool inside = sqrt(ex[K - 1]) * (1.0 + 1e-12) + (double)delta < (double)anchor.w;
     return full && clear && inside;
 }
