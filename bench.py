@@ -23,8 +23,9 @@ K_F, K_U = 16, 8
 ALPHAS = (1.0, 0.2, 1.0)
 
 
-def algorithmic_bytes(k_f=K_F, k_u=K_U):
+def algorithmic_bytes(k_f=None, k_u=None):
     """compulsory bytes per point per launch of each kernel (fp32 x3 vectors, int32 indices)."""
+    k_f, k_u = K_F if k_f is None else k_f, K_U if k_u is None else k_u
     return {
         "knn": 12 + 12 + 4 * k_f,                    # query, tree point, neighbour row out
         "nvt_smooth": 4 * k_f + 12 + 12 + 12,        # row in, position, normal, smoothed normal out
@@ -185,9 +186,13 @@ def run_reference(args):
 
 
 def workload_config(args, n):
-    return {"workload": "BASELINE.json configs[3]: synthetic 100M-point noisy CAD-like surface (cube faces 60 % + torus 40 %, isotropic Gaussian noise "
-                        "sigma = 0.3 x mean 6-NN distance, shuffled), k=16/8; one Processor.denoise iteration body per step; the whole cloud "
-                        "fits one B200 (37 GB), more GPUs split the same cloud into Morton slabs",
+    name = ("BASELINE.json configs[3]: synthetic 100M-point noisy CAD-like surface (cube faces 60 % + torus 40 %, isotropic Gaussian noise "
+            f"sigma = 0.3 x mean 6-NN distance, shuffled), k={K_F}/{K_U}; one Processor.denoise iteration body per step; the whole cloud "
+            "fits one B200 (37 GB), more GPUs split the same cloud into Morton slabs")
+    if K_F == 32:
+        name = ("BASELINE.json configs[2] stand-in (xyzrgb_dragon is a missing blob, SURVEY 8d): the synthetic creased surface at "
+                f"{n} points, Gaussian noise, k={K_F}/{K_U}, one Processor.denoise iteration body per step")
+    return {"workload": name,
             "points": n, "k_feature": K_F, "k_update": K_U, "strategy": "flat/edge/feature", "alpha": list(ALPHAS),
             "l2": "inputs larger than L2 (positions+normals+neighbour table >> 126 MB); no flush needed",
             "partition": "single GPU" if args.gpus == 1 else f"{args.gpus} Morton slabs + halo exchange"}
@@ -369,6 +374,7 @@ def run_ours(args):
 
 
 def main():
+    global K_F, K_U
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -379,7 +385,10 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-knn", action="store_true")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--k-feature", type=int, default=K_F, help="k of the feature pass (configs[2]: 32)")
+    ap.add_argument("--k-update", type=int, default=K_U)
     args = ap.parse_args()
+    K_F, K_U = args.k_feature, args.k_update
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)

@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libngpd.so")
+LIB_PATH = os.environ.get("NGPD_LIBRARY") or os.path.join(_HERE, "libngpd.so")   # NGPD_LIBRARY: another build of the same library (A/B timing)
 
 c_i64, c_i32, c_f32, c_vp = ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_void_p
 

@@ -124,7 +124,7 @@ __device__ __forceinline__ void session_write_row(int64_t s, int k, const int (&
 
 // tier 0: every row whose stored candidates still answer the query; the others are listed for the search tiers
 template <int K>
-__global__ void __launch_bounds__(128, 5) session_knn_rerank_kernel(GridView g, const float4* __restrict__ pos, const uint8_t* __restrict__ owned,
+__global__ void __launch_bounds__(128, K <= 16 ? 5 : 4) session_knn_rerank_kernel(GridView g, const float4* __restrict__ pos, const uint8_t* __restrict__ owned,
                                                                  int64_t n, int k, int32_t* __restrict__ idx, KnnTrack tr,
                                                                  int32_t* __restrict__ fail_list, int32_t* __restrict__ fail_count) {
     __shared__ KsCandTile<2 * K> tile;
@@ -229,14 +229,21 @@ __global__ void __launch_bounds__(128) session_knn_fix_kernel(GridView g, const 
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
         const int64_t s = fix_list[i];
         const float4 q = __ldg(pos + s);
-        TopK<KT> top;
+        // A 64-entry fp64 list lives in local memory (measured: 1.8 ms for a handful of rows) and a 48-entry one at 255
+        // registers is not much better (1.3 ms for 100 rows): with K = 32 only the row itself is searched here and nothing is
+        // stored for tier 0 (radius 0 = the row goes through the search tiers again next time; ~0.04 % of the rows, the ones
+        // in regions dense enough to overflow the 5x5x5 tier's range slots).
+        constexpr int KS = (KT > 32 && K <= 32) ? K : KT;
+        TopK<KS> top;
         top.init();
-        knn_search<KT>(top, g, (double)q.x, (double)q.y, (double)q.z, -1);
+        knn_search<KS>(top, g, (double)q.x, (double)q.y, (double)q.z, -1);
         int32_t* row = idx + s * k;
 #pragma unroll
         for (int a = 0; a < K; ++a)
             if (a < k) row[a] = top.id[a] >= 0 ? top.id[a] : (int32_t)s;   // fewer than k tree points: pad with self
-        if (KT > K) {
+        if constexpr (KT > K && KS < KT) {
+            tr.anchor[s] = make_float4(q.x, q.y, q.z, 0.0f);
+        } else if constexpr (KT > K) {
             int4* crow = reinterpret_cast<int4*>(tr.cand + s * KT);
 #pragma unroll
             for (int a = 0; a < KT / 4; ++a) crow[a] = make_int4(top.id[4 * a], top.id[4 * a + 1], top.id[4 * a + 2], top.id[4 * a + 3]);
@@ -304,7 +311,7 @@ __global__ void __launch_bounds__(128) session_nvt_smooth_late_kernel(Quad4 pos,
 // leaves, per block, {sum x, sum y, sum z, count} over the first ku neighbours of the rows it labelled sum_key
 // (flat_step's centre, Denoiser.py:106): the positions were just gathered, so the separate pass over the class is saved.
 template <int K>
-__global__ void __launch_bounds__(128, K == 16 ? 9 : 1) session_nvt_classify_kernel(Quad4 pos, Quad4 fn, const uint8_t* __restrict__ owned,
+__global__ void __launch_bounds__(128, K == 16 ? 9 : (K == 32 ? 6 : 1)) session_nvt_classify_kernel(Quad4 pos, Quad4 fn, const uint8_t* __restrict__ owned,
                                                                    const int32_t* __restrict__ idx, int64_t n, int k, float x_thresh,
                                                                    float scale, uint8_t* __restrict__ label, float4* __restrict__ edge,
                                                                    int sum_key, int ku, double* __restrict__ part, int32_t* __restrict__ cls) {
@@ -638,7 +645,7 @@ static int run_knn_fast(ngpd_session* S, int k, int32_t* idx, cudaStream_t st, b
     const GridView& g = S->grid->v;
     KnnLists L(S);
     NGPD_CUDA_OK(cudaMemsetAsync(L.cnt[0], 0, 3 * sizeof(int32_t), st));
-    constexpr bool CAN_TRACK = K <= 16;                      // 2K keys per lane must stay in registers
+    constexpr bool CAN_TRACK = K <= 32;                      // 2K keys per lane must stay in registers (K = 32: 64 keys at 2 blocks per SM)
     const bool rerank_ok = S->use_rerank && CAN_TRACK;
     if (track && rerank_ok && S->cand_k != K) {
         // first search with this row length: (re)allocate the candidate rows, no anchors yet

@@ -500,7 +500,7 @@ def _session_table(ng, sess, k):
     return out
 
 
-@pytest.mark.parametrize("k_f,k_u", [(16, 8), (8, 8)])
+@pytest.mark.parametrize("k_f,k_u", [(16, 8), (8, 8), (32, 8)])
 def test_knn_rerank_tier_is_exact(ng, k_f, k_u):
     """Temporal coherence: after the first search most rows are answered by re-ranking the stored candidates (tier 0).
     Every iteration's neighbour table must equal the exact shell search's, also after positions were replaced from
