@@ -80,12 +80,18 @@ class Processor:
     def denoise(self):
         """(:119-139) d = 2 * mean 6-NN edge length; two iterations; flat / edge / feature steps with
         alpha (1, .2, 1); positions are updated in place, graph.n becomes the smoothed normals."""
+        self._denoise_fused(16, 8, 2)
+
+    def _denoise_fused(self, k_feature: int, k_update: int, iterations: int):
+        """The loop of `denoise` on the fused session with the neighbourhood sizes as parameters (the reference hard-codes
+        16 / 8 / 2, :113, :126, :123; BASELINE configs[2] asks for k = 32)."""
         g = self.graph
         sess = self._get_session()
         sess.set_state(g.pos, g.n)
         d = 2.0 * self._mean_edge_length(6)
-        params = _lib.make_params(16, 8, None, 0.3, 3.0, 0.2, (_lib.STEP_FLAT, _lib.STEP_EDGE, _lib.STEP_FEATURE), (1.0, 0.2, 1.0), d)
-        for _ in range(2):
+        params = _lib.make_params(k_feature, k_update, None, 0.3, 3.0, 0.2, (_lib.STEP_FLAT, _lib.STEP_EDGE, _lib.STEP_FEATURE),
+                                  (1.0, 0.2, 1.0), d)
+        for _ in range(iterations):
             sess.step(params)
         pos, nrm, _ = sess.get_state(False)
         g.pos.copy_(pos)
@@ -151,17 +157,17 @@ class Processor:
             g.pos[indices] = new_pos
         return f_n
 
-    def denoise_unfused(self):
+    def denoise_unfused(self, k_feature: int = 16, k_update: int = 8, iterations: int = 2):
         """Processor.denoise written against the public operators, call for call as the reference does it
         (:119-139); used to cross-check the fused session."""
         g = self.graph
         l = TorchUtils.averageEdgeLength(g.pos, self.selector.getKNNSelection(6).getEdgeIndex())
         d = float(2 * l)
         alphas = [1, 0.2, 1]
-        for _ in range(2):
-            decomposition, f_n = self.getMyFeatureDecomposition()
+        for _ in range(iterations):
+            decomposition, f_n = self.getMyFeatureDecomposition(k_feature)
             classes = decomposition.getClasses()
-            selection = self.selector.getKNNSelection(8)
+            selection = self.selector.getKNNSelection(k_update)
             for key in range(3):
                 indices = (classes == key).nonzero().flatten()
                 if indices.size(0) == 0:

@@ -122,7 +122,10 @@ __device__ __forceinline__ void session_write_row(int64_t s, int k, const int (&
     }
 }
 
-// tier 0: every row whose stored candidates still answer the query; the others are listed for the search tiers
+// tier 0: every row whose stored candidates still answer the query; the others are listed for the search tiers.
+// (Measured and dropped: staging the window of 512-768 tree points around the block's rows in shared memory and gathering
+// the candidates' coordinates from there when they fall inside it -- 1.00 -> 1.17 ms at 10 M points, k = 16: the extra
+// select per candidate costs more than the L1 look-ups it saves.  6 instead of 5 blocks per SM (80 registers): no change.)
 template <int K>
 __global__ void __launch_bounds__(128, K <= 16 ? 5 : 4) session_knn_rerank_kernel(GridView g, const float4* __restrict__ pos, const uint8_t* __restrict__ owned,
                                                                  int64_t n, int k, int32_t* __restrict__ idx, KnnTrack tr,

@@ -340,6 +340,17 @@ def test_denoise_fused_equals_unfused(ng, fandisk):
     assert angle_between(a.graph.n.cpu().numpy(), b.graph.n.cpu().numpy()).max() < 1e-4
 
 
+@pytest.mark.parametrize("k_f,k_u", [(32, 8), (8, 6), (64, 16), (12, 5)])
+def test_denoise_fused_equals_unfused_other_neighbourhoods(ng, fandisk, k_f, k_u):
+    """The fused session against the per-stage public operators for the neighbourhood sizes of BASELINE configs[2] (k = 32),
+    the notebooks (64) and sizes without a specialised kernel (12 / 5): same labels' effect on positions, same normals."""
+    a = _fandisk_processor(ng, fandisk); a._denoise_fused(k_f, k_u, 2)
+    b = _fandisk_processor(ng, fandisk); b.denoise_unfused(k_f, k_u, 2)
+    scale = float(a.graph.pos.abs().max())
+    assert float((a.graph.pos - b.graph.pos).abs().max()) / scale < 2e-6
+    assert angle_between(a.graph.n.cpu().numpy(), b.graph.n.cpu().numpy()).max() < 1e-4
+
+
 def test_denoise_vs_reference_free_running(ng, fandisk):
     """Processor.denoise() end to end against the reference's result.  The reference's smoothing depends on LAPACK's
     eigenvector signs inside rank-deficient tensors (a 1-ulp change of its own input moves 0.82 % of its normals by
