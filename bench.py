@@ -202,7 +202,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     import ngpd_b200
-    from ngpd_b200 import _lib
+    from ngpd_b200 import _lib, partition
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -262,12 +262,14 @@ def run_ours(args):
 
     # ---- end to end through the host-buffer entry point: pinned host -> device, one iteration, device -> host
     e2e = None
+    # (pinned buffers are allocated on the GPU's own NUMA node: partition.near_gpu)
     if world == 1:
-        pos_h = torch.empty((n, 3), dtype=torch.float32).pin_memory()
-        nrm_h = torch.empty((n, 3), dtype=torch.float32).pin_memory()
-        pos_o = torch.empty((n, 3), dtype=torch.float32).pin_memory()
-        nrm_o = torch.empty((n, 3), dtype=torch.float32).pin_memory()
-        lab_o = torch.empty(n, dtype=torch.uint8).pin_memory()
+        with partition.near_gpu(dev.index) as cpus:
+            pos_h = torch.empty((n, 3), dtype=torch.float32).pin_memory()
+            nrm_h = torch.empty((n, 3), dtype=torch.float32).pin_memory()
+            pos_o = torch.empty((n, 3), dtype=torch.float32).pin_memory()
+            nrm_o = torch.empty((n, 3), dtype=torch.float32).pin_memory()
+            lab_o = torch.empty(n, dtype=torch.uint8).pin_memory()
         p, q, _ = sess.get_state(False)
         pos_h.copy_(p); nrm_h.copy_(q)
         del p, q
@@ -287,7 +289,9 @@ def run_ours(args):
         k = slab.n_owned
         _, p, q, _ = slab.owned_state()
         pin = lambda *shape, dtype=torch.float32: torch.empty(shape, dtype=dtype).pin_memory()
-        pos_h, nrm_h, pos_o, nrm_o, lab_o = pin(k, 3), pin(k, 3), pin(k, 3), pin(k, 3), pin(k, dtype=torch.uint8)
+        with partition.near_gpu(dev.index) as cpus:
+            pos_h, nrm_h, pos_o, nrm_o, lab_o = pin(k, 3), pin(k, 3), pin(k, 3), pin(k, 3), pin(k, dtype=torch.uint8)
+        print(f"[bench] rank {rank}: pinned staging allocated on the CPUs next to cuda:{dev.index}: {len(cpus)} of {os.cpu_count()}", file=sys.stderr)
         pos_h.copy_(p); nrm_h.copy_(q)
         del p, q
         e_steps = max(2, min(args.steps, 5))

@@ -16,7 +16,9 @@ and only halo VALUES travel:
 `SlabSession` binds them to the CUDA session."""
 from __future__ import annotations
 
+import contextlib
 import math
+import os
 
 import torch
 import torch.distributed as dist
@@ -149,6 +151,40 @@ def estimate_halo_width(tree_pos: torch.Tensor, k: int, factor: float = 6.0) -> 
         area = float(ext.max()) ** 2
     spacing = math.sqrt(area / tree_pos.size(0))
     return factor * spacing * math.sqrt(k / math.pi)
+
+
+# ------------------------------------------------------------------------------------------------------
+# host staging next to the GPU
+# ------------------------------------------------------------------------------------------------------
+def gpu_local_cpus(device_index: int) -> set[int]:
+    """CPUs on the NUMA node the GPU hangs off (NVML's ideal CPU affinity), restricted to the CPUs this process may use.
+    Empty when NVML or the topology says nothing."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+        h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        return cpus & os.sched_getaffinity(0)
+    except Exception:
+        return set()
+
+
+@contextlib.contextmanager
+def near_gpu(device_index: int):
+    """Run the body on the GPU's own NUMA node.  Pinned host buffers allocated inside land in that node's memory (first
+    touch), so their DMA does not cross the socket interconnect when one process per GPU runs on a multi-socket box.  A
+    no-op where NVML reports no affinity or the box has one node (the measured boxes: profiles/README.md, e2e note)."""
+    cpus = gpu_local_cpus(device_index)
+    before = os.sched_getaffinity(0)
+    if cpus:
+        os.sched_setaffinity(0, cpus)
+    try:
+        yield cpus
+    finally:
+        if cpus:
+            os.sched_setaffinity(0, before)
 
 
 # ------------------------------------------------------------------------------------------------------
