@@ -4,7 +4,6 @@ from __future__ import annotations
 
 import math
 
-import numpy as np
 import torch
 
 from . import _lib
@@ -90,7 +89,7 @@ class GraphBuilder:
 
     # ---- orientation (:129-209): edge cost 1-|ni.nj|, minimum spanning tree, propagate from the top-most point
     # flipping a child when n_parent.n_child < cos(7pi/12).  On the GPU (Boruvka rounds + breadth-first frontier,
-    # csrc/orient.cu); flipNormalsHost is the SciPy version of the same definition, kept for cross-checks.
+    # csrc/orient.cu); there is no host version in this package (the SciPy cross-check lives in oracle/).
     def calculateEdgeCost(self) -> None:
         g = self.graph
         GeneralUtils.validateAttributes(g, ["edge_index", "n"])
@@ -111,33 +110,3 @@ class GraphBuilder:
                                                    math.cos(7.0 / 12.0 * math.pi), info, _lib.stream()), "ngpd_orient_normals")
         self.orientation_info = {"components": info[0], "levels": info[1], "rounds": info[2]}
         g.n = nrm
-
-    def flipNormalsHost(self) -> None:
-        from scipy.sparse import coo_matrix
-        from scipy.sparse.csgraph import breadth_first_order, minimum_spanning_tree
-
-        self.calculateEdgeCost()
-        g = self.graph
-        n = g.num_nodes
-        ei = g.edge_index.cpu().numpy()
-        # csgraph treats explicit zeros as missing edges: shift the costs into (0, 2]
-        cost = g.edge_attr.double().cpu().numpy() + 1e-9
-        lo, hi = np.minimum(ei[0], ei[1]), np.maximum(ei[0], ei[1])
-        order = np.lexsort((cost, hi, lo))
-        lo, hi, cost = lo[order], hi[order], cost[order]
-        first = np.ones(len(lo), dtype=bool)
-        first[1:] = (lo[1:] != lo[:-1]) | (hi[1:] != hi[:-1])
-        mst = minimum_spanning_tree(coo_matrix((cost[first], (lo[first], hi[first])), shape=(n, n)).tocsr())
-        mst = (mst + mst.T).tocsr()
-        nrm = g.n.detach().cpu().numpy().copy()
-        pos = g.pos.detach().cpu().numpy()
-        thr = math.cos(7.0 / 12.0 * math.pi)
-        root = int(np.argmax(pos[:, 2]))
-        if nrm[root, 2] < 0:
-            nrm[root] *= -1
-        visit, parent = breadth_first_order(mst, root, directed=False, return_predecessors=True)
-        for v in visit[1:]:
-            p = parent[v]
-            if float((nrm[p] * nrm[v]).sum(dtype=np.float32)) < thr:
-                nrm[v] *= -1
-        g.n = torch.from_numpy(nrm).to(g.pos.device)

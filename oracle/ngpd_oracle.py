@@ -444,6 +444,35 @@ def orient_normals(pos, nrm, nbr):
     return n
 
 
+def orient_normals_scipy(pos, nrm, edge_index):
+    """The same definition through SciPy's csgraph (another tie order among equal-cost edges than the Kruskal above):
+    edge_index [2, E] as the mirror's GraphBuilder.getKNNEdgeIndex returns it.  Cross-check only."""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import breadth_first_order, minimum_spanning_tree
+    pos = np.asarray(pos, dtype=F32); n = np.array(nrm, dtype=F32, copy=True)
+    ei = np.asarray(edge_index)
+    N = len(pos)
+    # csgraph treats explicit zeros as missing edges: shift the costs into (0, 2]
+    cost = (F32(1) - np.abs(dot3(n[ei[0]], n[ei[1]]))).astype(np.float64) + 1e-9
+    lo, hi = np.minimum(ei[0], ei[1]), np.maximum(ei[0], ei[1])
+    order = np.lexsort((cost, hi, lo))
+    lo, hi, cost = lo[order], hi[order], cost[order]
+    first = np.ones(len(lo), dtype=bool)
+    first[1:] = (lo[1:] != lo[:-1]) | (hi[1:] != hi[:-1])
+    mst = minimum_spanning_tree(coo_matrix((cost[first], (lo[first], hi[first])), shape=(N, N)).tocsr())
+    mst = (mst + mst.T).tocsr()
+    thr = math.cos(7.0 / 12.0 * math.pi)
+    root = int(np.argmax(pos[:, 2]))
+    if n[root, 2] < 0:
+        n[root] *= -1
+    visit, parent = breadth_first_order(mst, root, directed=False, return_predecessors=True)
+    for v in visit[1:]:
+        p = parent[v]
+        if float((n[p] * n[v]).sum(dtype=np.float32)) < thr:
+            n[v] *= -1
+    return n
+
+
 # ------------------------------------------------------------------------------------------------
 # the iterate loop (Processor.getMyFeatureDecomposition :110-117, Processor.denoise :119-139)
 # ------------------------------------------------------------------------------------------------

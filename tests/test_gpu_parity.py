@@ -906,10 +906,8 @@ def test_orientation_vs_reference(ng, fandisk):
     assert agree > 0.97
     assert p.graphBuilder.orientation_info["components"] == 1
     # the SciPy version of the same definition (another tie order)
-    q = _knn_graph(ng, fandisk["pos0"], 12)
-    q.graph.n = cu(fandisk["n_pca"]).clone()
-    q.graphBuilder.flipNormalsHost()
-    assert ((n_gpu * q.graph.n.cpu().numpy()).sum(1) > 0).mean() > 0.97
+    n_scipy = O.orient_normals_scipy(fandisk["pos0"], fandisk["n_pca"], p.graph.edge_index.cpu().numpy())
+    assert ((n_gpu * n_scipy).sum(1) > 0).mean() > 0.97
 
 
 def test_orientation_unique_tree_equals_oracle(ng):
