@@ -213,6 +213,12 @@ int ngpd_session_set_owned(ngpd_session_t* s, const uint8_t* owned_tree_order, v
 void* ngpd_session_buffer(ngpd_session_t* s, int which);
 /* halo traffic: gather / scatter float4 rows of buffer `which` (0..2) listed by tree position */
 int ngpd_session_export_rows(ngpd_session_t* s, int which, const int32_t* rows, int64_t m, float* out4, void* stream);
+/* the same gather with the halo exchange fused in: row i of the list is stored directly into the receive buffer of the rank
+ * that needs it -- rows [seg[p], seg[p+1]) go to peer p, row seg[p] landing at address peer_base[p] (a float4 slot inside
+ * peer p's buffer, mapped into this process: CUDA IPC / symmetric memory over NVLink).  seg (world+1 entries) and peer_base
+ * (world entries) are device arrays.  The caller orders the peers' reads after the stores (a cross-rank barrier on the stream). */
+int ngpd_session_export_rows_peers(ngpd_session_t* s, int which, const int32_t* rows, int64_t m, const int64_t* seg,
+                                   const uint64_t* peer_base, int world, void* stream);
 int ngpd_session_import_rows(ngpd_session_t* s, int which, const int32_t* rows, int64_t m, const float* in4, void* stream);
 
 /* End-to-end entry points with HOST buffers (the path the e2e measurement times): copy this step's positions and

@@ -70,6 +70,7 @@ SIGNATURES = {
     "ngpd_session_order": (ctypes.c_int, [c_vp, c_vp, c_vp]),
     "ngpd_session_buffer": (c_vp, [c_vp, ctypes.c_int]),
     "ngpd_session_export_rows": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_i64, c_vp, c_vp]),
+    "ngpd_session_export_rows_peers": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_i64, c_vp, c_vp, ctypes.c_int, c_vp]),
     "ngpd_session_import_rows": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_i64, c_vp, c_vp]),
     "ngpd_session_run_host": (ctypes.c_int, [c_vp, ctypes.POINTER(StepParams), ctypes.c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ngpd_denoise_host": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, ctypes.POINTER(StepParams), ctypes.c_int, c_vp, c_vp, c_vp]),

@@ -583,6 +583,18 @@ __global__ void __launch_bounds__(256) session_export_kernel(const float4* __res
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < m) out[i] = src[rows[i]];
 }
+// the same gather, but every row goes straight into the receive buffer of the rank that needs it (peer memory mapped into
+// this process, stores travel over NVLink): rows [seg[p], seg[p+1]) belong to peer p and land at peer_base[p] onwards
+__global__ void __launch_bounds__(256) session_export_peers_kernel(const float4* __restrict__ src, const int32_t* __restrict__ rows, int64_t m,
+                                                                   const int64_t* __restrict__ seg, const unsigned long long* __restrict__ peer_base,
+                                                                   int world) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    int p = 0;
+    while (p + 1 < world && i >= seg[p + 1]) ++p;
+    float4* dst = reinterpret_cast<float4*>(peer_base[p]);
+    dst[i - seg[p]] = src[rows[i]];
+}
 __global__ void __launch_bounds__(256) session_import_kernel(float4* __restrict__ dst, const int32_t* __restrict__ rows, int64_t m,
                                                              const float4* __restrict__ in) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1061,6 +1073,15 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_export_rows(n
     if (m <= 0) return 0;
     const float4* src = which == 0 ? S->pos[S->cur] : (which == 1 ? S->nrm : S->fn);
     session_export_kernel<<<(unsigned)cdiv(m, 256), 256, 0, (cudaStream_t)stream_>>>(src, rows, m, (float4*)out4);
+    NGPD_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+extern "C" __attribute__((visibility("default"))) int ngpd_session_export_rows_peers(ngpd_session_t* S, int which, const int32_t* rows, int64_t m,
+                                                                                     const int64_t* seg, const uint64_t* peer_base, int world, void* stream_) {
+    NGPD_REQUIRE(S && (which >= 0 && which <= 2) && world >= 1 && (m <= 0 || (rows && seg && peer_base)), "ngpd_session_export_rows_peers: bad argument");
+    if (m <= 0) return 0;
+    const float4* src = which == 0 ? S->pos[S->cur] : (which == 1 ? S->nrm : S->fn);
+    session_export_peers_kernel<<<(unsigned)cdiv(m, 256), 256, 0, (cudaStream_t)stream_>>>(src, rows, m, seg, reinterpret_cast<const unsigned long long*>(peer_base), world);
     NGPD_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -137,6 +137,33 @@ class HaloExchanger:
         dist.all_to_all_single(recv_buf, send_buf, output_split_sizes=self.recv_counts, input_split_sizes=self.send_counts,
                                group=self.group)
 
+    # -- halo push over peer memory (opt-in: SlabSession(transport="peer")) ---------------------------------------------
+    def enable_peer_push(self, device: torch.device):
+        """Symmetric receive buffers (two, used alternately) that the peers' export kernels write into directly
+        (`ngpd_session_export_rows_peers`): one kernel + one cross-rank barrier per exchange instead of gather kernel ->
+        NCCL all-to-all -> scatter.  Double buffering: a peer may already be pushing exchange t+1 while this rank still
+        unpacks exchange t (the barrier only orders a rank's unpacking after everybody's pushing)."""
+        import torch.distributed._symmetric_memory as symm
+        world, rank = self.plan.world, self.plan.rank
+        group = self.group if self.group is not None else dist.group.WORLD
+        mine = torch.tensor(self.recv_counts, dtype=torch.long, device=device)
+        table = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(table, mine, group=group)
+        recv = [[int(v) for v in t.tolist()] for t in table]              # recv[q][s] = rows rank q receives from rank s
+        cap = max(1, max(sum(r) for r in recv))
+        self._sym = symm.empty((2, cap, 4), dtype=torch.float32, device=device)
+        self._hdl = symm.rendezvous(self._sym, group)
+        ptrs = [int(a) for a in self._hdl.buffer_ptrs]
+        # where this rank's rows start inside peer q's buffer b: after the rows of the lower ranks
+        self._peer_base = [torch.tensor([ptrs[q] + 16 * (b * cap + sum(recv[q][:rank])) for q in range(world)],
+                                        dtype=torch.int64, device=device) for b in range(2)]
+        seg = [0]
+        for c in self.send_counts:
+            seg.append(seg[-1] + c)
+        self._seg = torch.tensor(seg, dtype=torch.long, device=device)
+        self._parity = 0
+        self.peer = True
+
     def bytes_per_exchange(self, row_bytes: int = 16):
         return sum(self.send_counts) * row_bytes, sum(self.recv_counts) * row_bytes
 
@@ -201,7 +228,8 @@ class SlabSession:
     """One rank's share of a denoising run: owned slab + halo in one CUDA session, halos refreshed between phases."""
 
     def __init__(self, pos: torch.Tensor, nrm: torch.Tensor, k_feature=16, k_update=8, alphas=(1.0, 0.2, 1.0),
-                 strategy=None, halo_width: float | None = None, group=None, tree_pos: torch.Tensor | None = None):
+                 strategy=None, halo_width: float | None = None, group=None, tree_pos: torch.Tensor | None = None,
+                 transport: str | None = None):
         from . import _lib
         self._lib = _lib
         self.group = group
@@ -229,6 +257,13 @@ class SlabSession:
         self._recv_rows = torch.cat([inv[r] for r in self.ex.recv_local]).to(torch.int32).contiguous()
         self._send_buf = torch.empty((self._send_rows.numel(), 4), dtype=torch.float32, device=dev)
         self._recv_buf = torch.empty((self._recv_rows.numel(), 4), dtype=torch.float32, device=dev)
+        # halo transport: "nccl" = gather kernel + one all-to-all + scatter kernel; "peer" = the gather kernel stores into the
+        # peers' receive buffers itself (symmetric memory over NVLink) and a cross-rank barrier replaces the collective
+        transport = transport or os.environ.get("NGPD_HALO_TRANSPORT", "nccl")
+        assert transport in ("nccl", "peer"), transport
+        self.transport = transport if world > 1 else "nccl"
+        if self.transport == "peer":
+            self.ex.enable_peer_push(dev)
         self._inv = inv
         # global d = 2 * mean 6-NN edge length (Processor.py:120-121)
         s, c = self.session.mean_edge_length_parts(6)
@@ -247,6 +282,17 @@ class SlabSession:
             return
         lib, L = self._lib.load(), self._lib
         h = self.session._h
+        if self.transport == "peer":
+            ex = self.ex
+            b = ex._parity
+            ex._parity ^= 1
+            L.check(lib.ngpd_session_export_rows_peers(h, which, self._send_rows.data_ptr(), self._send_rows.numel(), ex._seg.data_ptr(),
+                                                       ex._peer_base[b].data_ptr(), self.world, L.stream()), "ngpd_session_export_rows_peers")
+            ex._hdl.barrier(channel=0)                          # every rank's stores have landed before anybody unpacks
+            L.check(lib.ngpd_session_import_rows(h, which, self._recv_rows.data_ptr(), self._recv_rows.numel(), ex._sym[b].data_ptr(), L.stream()),
+                    "ngpd_session_import_rows")
+            self.exchanges += 1
+            return
         L.check(lib.ngpd_session_export_rows(h, which, self._send_rows.data_ptr(), self._send_rows.numel(), self._send_buf.data_ptr(), L.stream()),
                 "ngpd_session_export_rows")
         self.ex.exchange(self._send_buf, self._recv_buf)
