@@ -150,22 +150,33 @@ class HaloExchanger:
         table = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(table, mine, group=group)
         recv = [[int(v) for v in t.tolist()] for t in table]              # recv[q][s] = rows rank q receives from rank s
-        cap = max(1, max(sum(r) for r in recv))
+        cap, first_row, seg = peer_push_layout(recv, rank)
+        assert seg[1:] == [sum(self.send_counts[:q + 1]) for q in range(world)]
         self._sym = symm.empty((2, cap, 4), dtype=torch.float32, device=device)
         self._hdl = symm.rendezvous(self._sym, group)
         ptrs = [int(a) for a in self._hdl.buffer_ptrs]
-        # where this rank's rows start inside peer q's buffer b: after the rows of the lower ranks
-        self._peer_base = [torch.tensor([ptrs[q] + 16 * (b * cap + sum(recv[q][:rank])) for q in range(world)],
+        self._peer_base = [torch.tensor([ptrs[q] + 16 * (b * cap + first_row[q]) for q in range(world)],
                                         dtype=torch.int64, device=device) for b in range(2)]
-        seg = [0]
-        for c in self.send_counts:
-            seg.append(seg[-1] + c)
         self._seg = torch.tensor(seg, dtype=torch.long, device=device)
         self._parity = 0
         self.peer = True
 
     def bytes_per_exchange(self, row_bytes: int = 16):
         return sum(self.send_counts) * row_bytes, sum(self.recv_counts) * row_bytes
+
+
+def peer_push_layout(recv: list[list[int]], rank: int):
+    """Addressing of the peer-memory halo push.  recv[q][s] = rows rank q receives from rank s (its receive buffer holds
+    them grouped by source, ascending).  Returns (rows per receive buffer -- the same on every rank, as symmetric memory
+    wants --, first_row[q] = row inside rank q's buffer where THIS rank's block starts, seg = prefix sums of this rank's
+    send counts: rows [seg[q], seg[q+1]) of its packed send list belong to rank q)."""
+    world = len(recv)
+    cap = max(1, max(sum(r) for r in recv))
+    first_row = [sum(recv[q][:rank]) for q in range(world)]
+    seg = [0]
+    for q in range(world):
+        seg.append(seg[-1] + recv[q][rank])
+    return cap, first_row, seg
 
 
 def estimate_halo_width(tree_pos: torch.Tensor, k: int, factor: float = 6.0) -> float:

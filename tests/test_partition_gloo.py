@@ -143,3 +143,34 @@ def test_morton_keys_order_is_spatial():
     step = (pos[order[1:]] - pos[order[:-1]]).norm(dim=1).mean()
     rand = (pos[1:] - pos[:-1]).norm(dim=1).mean()
     assert float(step) < 0.15 * float(rand)
+
+
+def test_peer_push_layout_emulated():
+    """Addressing of the peer-memory halo push (partition.peer_push_layout), emulated on the host for 4 ranks with ragged
+    counts: every rank stores its packed send rows at first_row[q] + (i - seg[q]) of peer q's buffer; afterwards each
+    buffer must hold, grouped by source rank in ascending order, exactly what an all-to-all would have delivered."""
+    from ngpd_b200.partition import peer_push_layout
+    rng = np.random.default_rng(3)
+    world = 4
+    recv = rng.integers(0, 9, size=(world, world))
+    np.fill_diagonal(recv, 0)
+    recv[2, :] = 0                                                       # a rank that receives nothing
+    recv = recv.tolist()
+    send_rows = {(s, q): [(s, q, j) for j in range(recv[q][s])] for s in range(world) for q in range(world)}
+    caps, buffers = set(), None
+    for s in range(world):
+        cap, first_row, seg = peer_push_layout(recv, s)
+        caps.add(cap)
+        if buffers is None:
+            buffers = [[None] * cap for _ in range(world)]
+        packed = [r for q in range(world) for r in send_rows[(s, q)]]    # this rank's send list, grouped by destination
+        assert seg[-1] == len(packed)
+        for i, row in enumerate(packed):
+            q = max(p for p in range(world) if seg[p] <= i and seg[p] < seg[p + 1] and i < seg[p + 1])
+            assert buffers[q][first_row[q] + i - seg[q]] is None          # nobody else writes this slot
+            buffers[q][first_row[q] + i - seg[q]] = row
+    assert len(caps) == 1                                                # symmetric: one size on every rank
+    for q in range(world):
+        want = [r for s in range(world) for r in send_rows[(s, q)]]
+        assert buffers[q][:len(want)] == want
+        assert all(v is None for v in buffers[q][len(want):])
