@@ -660,7 +660,7 @@ static int run_knn_fast(ngpd_session* S, int k, int32_t* idx, cudaStream_t st, b
     const GridView& g = S->grid->v;
     KnnLists L(S);
     NGPD_CUDA_OK(cudaMemsetAsync(L.cnt[0], 0, 3 * sizeof(int32_t), st));
-    constexpr bool CAN_TRACK = K <= 32;                      // 2K keys per lane must stay in registers (K = 32: 64 keys at 2 blocks per SM)
+    constexpr bool CAN_TRACK = K <= 32;                      // 2K keys per lane must stay in registers (K = 32: 64 keys, 128 registers, 4 blocks per SM)
     const bool rerank_ok = S->use_rerank && CAN_TRACK;
     if (track && rerank_ok && S->cand_k != K) {
         // first search with this row length: (re)allocate the candidate rows, no anchors yet
