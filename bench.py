@@ -364,9 +364,9 @@ def run_ours(args):
                 "iteration_frac": bytes_per["iteration"] * n / (ms / args.steps * 1e-3) / 1e9 / peak}
     cpu = None
     if world == 1 and not args.no_cpu:
-        v, cores, per_it = cpu_iteration_rate(args.cpu_points, 2)
+        v, cores, per_it = cpu_iteration_rate(args.cpu_points, 5)          # ~11 s of CPU work at 200 k points
         cpu = {"value": v, "unit": "point-iterations/s", "cores": cores, "kind": "port",
-               "sample": f"{args.cpu_points}-point cloud from the same generator, 1 warm-up + 2 timed iterations of the oracle port "
+               "sample": f"{args.cpu_points}-point cloud from the same generator, 1 warm-up + 5 timed iterations of the oracle port "
                          f"(NumPy + SciPy KD-tree workers=-1 + LAPACK), {per_it:.2f} s per iteration"}
     line = {"metric": "denoise point-iterations/sec (kNN+NVT+update)", "value": value, "unit": "point-iterations/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
