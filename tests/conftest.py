@@ -39,6 +39,13 @@ def cpsd():
     return dict(np.load(os.path.join(GOLDEN, "cpsd_fandisk.npz")))
 
 
+@pytest.fixture(scope="session")
+def fandisk_k32():
+    """Processor.getMyFeatureDecomposition(32) + class steps on fandisk, recorded from the reference (make_golden_k32.py)"""
+    import numpy as np
+    return dict(np.load(os.path.join(GOLDEN, "fandisk_k32.npz")))
+
+
 def angle_between(a, b):
     """fp64 atan2(|a x b|, a.b): fp32 acos has a ~5e-4 rad floor near 0."""
     import numpy as np

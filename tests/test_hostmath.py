@@ -69,6 +69,26 @@ def test_tensor_eig_smooth_labels(hm, fandisk, it):
     assert np.array_equal(lab, fandisk[t + "classes"])                            # labels bit-exact from own eigenvalues
 
 
+def test_tensor_eig_labels_k32(hm, fandisk, fandisk_k32):
+    """The kernels' per-point math at BASELINE configs[2]'s neighbourhood size (k = 32), against the reference's tensors."""
+    g = fandisk_k32
+    n = len(fandisk["pos0"])
+    pos, nrm, idx = (np.ascontiguousarray(a) for a in (fandisk["pos0"], fandisk["n_flip"], g["knn32"]))
+    w = np.zeros((n, 3), np.float32); V = np.zeros((n, 3, 3), np.float32); T = np.zeros((n, 3, 3), np.float32); sw = np.zeros(n, np.int32)
+    hm.hm_nvt(P(pos), P(nrm), P(idx), None, ctypes.c_int64(n), 32, xt(), P(w), P(V), P(T), P(sw))
+    assert np.array_equal(T, g["T1"])
+    assert np.abs(w - g["eigval1"]).max() < 1e-6
+    out = np.zeros((n, 3), np.float32)
+    hm.hm_smooth(P(w), P(V), P(nrm), ctypes.c_int64(n), ctypes.c_float(0.3), ctypes.c_float(3.0), P(out))
+    assert (angle_between(out, g["f_n"]) > 1e-4).mean() < 0.0082              # the reference's own 1-ulp noise floor
+    fn = np.ascontiguousarray(g["f_n"])
+    hm.hm_nvt(P(pos), P(fn), P(idx), None, ctypes.c_int64(n), 32, xt(), P(w), P(V), P(T), P(sw))
+    assert np.array_equal(T, g["T2"])
+    lab = np.zeros(n, np.uint8)
+    hm.hm_classify(P(w), ctypes.c_int64(n), ctypes.c_float(0.2), P(lab))
+    assert np.array_equal(lab, g["classes"])
+
+
 @pytest.mark.parametrize("it", [0, 1])
 def test_updates(hm, fandisk, it):
     t = f"it{it}_"

@@ -65,6 +65,25 @@ def test_nvt_smooth_classify(fandisk, it):
     assert np.allclose(np.stack([pla, lin, sph], 1), fandisk[t + "features"], rtol=0, atol=1e-6)
 
 
+def test_k32_decomposition_and_steps(fandisk, fandisk_k32):
+    """BASELINE configs[2]'s neighbourhood size: the 32-NN table, both voting tensors, smoothed normals, labels and the three
+    class steps of one iteration against the reference's Processor.getMyFeatureDecomposition(32)."""
+    g = fandisk_k32
+    pos, nrm = fandisk["pos0"], fandisk["n_flip"]
+    nbr = O.knn_bruteforce(pos, pos, 32)
+    assert O.tie_groups_equal(pos, pos, nbr, g["knn32"].astype(np.int64))
+    nbr = g["knn32"]
+    rows = np.arange(len(pos))
+    xt = O.acos_threshold(RHO)
+    w1, V1, T1, _ = O.nvt(pos, nrm, rows, nbr, xt)
+    assert np.array_equal(T1, g["T1"]) and np.array_equal(w1, g["eigval1"]) and np.array_equal(V1, g["eigvec1"])
+    assert angle_between(O.smooth_normals(w1, V1, nrm), g["f_n"]).max() < 1e-6
+    w2, V2, T2, _ = O.nvt(pos, g["f_n"], rows, nbr, xt)
+    assert np.array_equal(T2, g["T2"]) and np.array_equal(O.classes(w2), g["classes"])
+    out, _, _, _ = O.denoise_iteration(pos, pos, nrm, 32, 8, xt, (1.0, 0.2, 1.0), np.float32(2) * g["l"], knn=O.knn_bruteforce)
+    assert np.abs(out - g["pos_after"]).max() / np.abs(g["pos_after"]).max() < 1e-5
+
+
 @pytest.mark.parametrize("it", [0, 1])
 def test_update_steps(fandisk, it):
     t = f"it{it}_"
