@@ -43,6 +43,11 @@ class Decomposition:
     def getVUFeatures(self, tau: float) -> torch.Tensor:
         return (self.eigval < tau).sum(dim=1) % 3
 
+    def getBetterVUFeatures(self, mean_graph_edge_length: float, k: int = 6) -> torch.Tensor:
+        """(:87-90) the same count with the threshold scaled to the cloud: tau = 16 / k * l^2."""
+        tau = 16.0 / k * mean_graph_edge_length ** 2
+        return (self.eigval < tau).sum(dim=1) % 3
+
     def getVUSmoothedNormals(self, n: torch.Tensor, tau: float = 0.3, d: float = 3) -> torch.Tensor:
         """Eigen-space smoothing exactly as the reference evaluates it (:92-106), eigenvector signs included."""
         ev = _lib.dev(self.eigval, torch.float32, "eigval")

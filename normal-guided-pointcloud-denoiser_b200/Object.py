@@ -55,6 +55,64 @@ def sample_points(pos: torch.Tensor, face: torch.Tensor, num: int):
     return pos_sampled * pos_max, normal
 
 
+_PLY_TYPES = {"char": "i1", "int8": "i1", "uchar": "u1", "uint8": "u1", "short": "i2", "int16": "i2", "ushort": "u2", "uint16": "u2",
+              "int": "i4", "int32": "i4", "uint": "u4", "uint32": "u4", "float": "f4", "float32": "f4", "double": "f8", "float64": "f8"}
+
+
+def read_ply_vertices(file_path: str) -> np.ndarray:
+    """x, y, z of the `vertex` element of a PLY file as [N,3] float64 (ascii, binary_little_endian or binary_big_endian;
+    other properties and elements are skipped).  The reference reads the same through Open3D (Object.py:128)."""
+    with open(file_path, "rb") as fh:
+        if fh.readline().strip() != b"ply":
+            raise ValueError(f"{file_path}: not a PLY file")
+        fmt, elements = None, []                       # elements: [name, count, [(property name, dtype or ("list", count type, item type))]]
+        while True:
+            line = fh.readline()
+            if not line:
+                raise ValueError(f"{file_path}: header without end_header")
+            tok = line.decode("ascii", "replace").split()
+            if not tok or tok[0] in ("comment", "obj_info"):
+                continue
+            if tok[0] == "format":
+                fmt = tok[1]
+            elif tok[0] == "element":
+                elements.append([tok[1], int(tok[2]), []])
+            elif tok[0] == "property":
+                if tok[1] == "list":
+                    elements[-1][2].append((tok[4], ("list", _PLY_TYPES[tok[2]], _PLY_TYPES[tok[3]])))
+                else:
+                    elements[-1][2].append((tok[2], _PLY_TYPES[tok[1]]))
+            elif tok[0] == "end_header":
+                break
+        if fmt not in ("ascii", "binary_little_endian", "binary_big_endian"):
+            raise ValueError(f"{file_path}: unknown PLY format {fmt!r}")
+        for name, count, props in elements:
+            scalar = all(not isinstance(t, tuple) for _, t in props)
+            if name != "vertex":
+                # skip the element: only possible without parsing when every property has a fixed size
+                if fmt == "ascii":
+                    for _ in range(count):
+                        fh.readline()
+                elif scalar:
+                    fh.seek(count * sum(np.dtype(t).itemsize for _, t in props), 1)
+                else:
+                    raise ValueError(f"{file_path}: a list element precedes the vertices")
+                continue
+            if not scalar:
+                raise ValueError(f"{file_path}: list property inside the vertex element")
+            names = [n for n, _ in props]
+            if not all(a in names for a in ("x", "y", "z")):
+                raise ValueError(f"{file_path}: vertex element without x, y, z")
+            if fmt == "ascii":
+                rows = np.loadtxt(fh, dtype=np.float64, max_rows=count, ndmin=2) if count else np.zeros((0, len(names)))
+                return np.stack([rows[:, names.index(a)] for a in ("x", "y", "z")], axis=1).reshape(-1, 3)
+            end = "<" if fmt == "binary_little_endian" else ">"
+            rec = np.dtype([(n, end + t) for n, t in props])
+            data = np.frombuffer(fh.read(count * rec.itemsize), dtype=rec, count=count)
+            return np.stack([data[a].astype(np.float64) for a in ("x", "y", "z")], axis=1).reshape(-1, 3)
+    raise ValueError(f"{file_path}: no vertex element")
+
+
 class Pointcloud:
     def __init__(self, v: torch.Tensor, n: torch.Tensor = None) -> None:
         assert v.is_floating_point()
@@ -105,6 +163,18 @@ class Pointcloud:
             pc = cls(vt, torch.tensor(vn, dtype=torch.float, device=device))
         else:
             pc = cls(vt)
+        pc.file_path = file_path
+        return pc
+
+    @classmethod
+    def loadPly(cls, file_path: str, device=None) -> "Pointcloud":
+        """Object.py:119-132: positions of a .ply point cloud (no normals, like the reference); self-contained reader
+        instead of Open3D."""
+        path = Path(file_path)
+        assert path.is_file()
+        assert path.suffix == ".ply"
+        device = device if device is not None else _default_device()
+        pc = cls(torch.tensor(read_ply_vertices(file_path), dtype=torch.float, device=device))
         pc.file_path = file_path
         return pc
 

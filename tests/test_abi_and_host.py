@@ -144,3 +144,50 @@ def test_sample_obj_properties(tmp_path):
     torch.manual_seed(0)
     again = ng.Pointcloud.sampleObj(str(obj), 20000, device="cpu")
     assert torch.equal(again.v, pc.v) and torch.equal(again.n, pc.n)
+
+
+@pytest.mark.parametrize("fmt", ["ascii", "binary_little_endian", "binary_big_endian"])
+def test_ply_loader(tmp_path, fmt):
+    """Pointcloud.loadPly (Object.py:119-132; the reference goes through Open3D): ascii and both binary layouts, extra vertex
+    properties in between, a face element after the vertices, comments in the header."""
+    import torch
+    import ngpd_b200 as ng
+    rng = np.random.default_rng(5)
+    n = 257
+    xyz = rng.normal(size=(n, 3)).astype(np.float32)
+    red = rng.integers(0, 255, n).astype(np.uint8)
+    nx = rng.normal(size=n)
+    header = ["ply", f"format {fmt} 1.0", "comment made by a test", f"element vertex {n}", "property float x", "property uchar red",
+              "property float y", "property double nx", "property float z", "element face 1", "property list uchar int vertex_indices",
+              "end_header"]
+    path = tmp_path / "cloud.ply"
+    with open(path, "wb") as fh:
+        fh.write(("\n".join(header) + "\n").encode("ascii"))
+        if fmt == "ascii":
+            for i in range(n):
+                # repr of the fp32 value widened to a Python float round-trips exactly
+                fh.write(f"{float(xyz[i, 0])!r} {int(red[i])} {float(xyz[i, 1])!r} {float(nx[i])!r} {float(xyz[i, 2])!r}\n".encode("ascii"))
+            fh.write(b"3 0 1 2\n")
+        else:
+            e = "<" if fmt == "binary_little_endian" else ">"
+            rec = np.zeros(n, dtype=[("x", e + "f4"), ("red", "u1"), ("y", e + "f4"), ("nx", e + "f8"), ("z", e + "f4")])
+            rec["x"], rec["red"], rec["y"], rec["nx"], rec["z"] = xyz[:, 0], red, xyz[:, 1], nx, xyz[:, 2]
+            fh.write(rec.tobytes())
+            fh.write(np.array([3], "u1").tobytes() + np.array([0, 1, 2], e + "i4").tobytes())
+    pc = ng.Pointcloud.loadPly(str(path), device="cpu")
+    assert pc.v.dtype == torch.float32 and tuple(pc.v.shape) == (n, 3) and pc.n is None
+    assert np.array_equal(pc.v.numpy(), xyz)
+    assert pc.file_path == str(path)
+    with pytest.raises(AssertionError):
+        ng.Pointcloud.loadPly(str(tmp_path / "cloud.obj"))
+
+
+def test_better_vu_features():
+    import torch
+    import ngpd_b200 as ng
+    w = torch.tensor([[0.0, 0.1, 0.9], [0.5, 0.6, 0.7], [0.0, 0.0, 0.01], [0.0, 0.2, 0.21]])
+    dec = ng.Decomposition(w, torch.eye(3).repeat(4, 1, 1))
+    l, k = 0.25, 6
+    tau = 16.0 / k * l ** 2                                          # 0.1667
+    assert torch.equal(dec.getBetterVUFeatures(l, k), (w < tau).sum(1) % 3)
+    assert dec.getBetterVUFeatures(l, k).tolist() == [2, 0, 0, 1]
