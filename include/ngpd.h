@@ -160,7 +160,13 @@ typedef struct ngpd_step_params {
     int32_t strategy[3];     /* NGPD_STEP_* per label; -1 = leave the class alone */
     float alpha[3];
     float dmax;
+    int32_t flags;           /* NGPD_STEP_SNAPSHOT_CLASSES or 0 */
+    float clamp_radius;      /* > 0 (with ngpd_session_set_original): a new position is kept only while
+                                |x_new - x_original| < clamp_radius, PostProcessing.ipynb#c9 "Ours" / "CPSD" */
 } ngpd_step_params_t;
+/* flags: every class is moved from the SAME snapshot of the positions (the notebook's temp_pos loop, PostProcessing.ipynb#c9)
+ * instead of one class after the other in place (Processor.py:127-138, the default) */
+#define NGPD_STEP_SNAPSHOT_CLASSES 1
 
 int ngpd_session_create(const float* tree_pos, int64_t n, int k_hint, void* stream, ngpd_session_t** out);
 int ngpd_session_destroy(ngpd_session_t* s);
@@ -172,8 +178,9 @@ int ngpd_session_step(ngpd_session_t* s, const ngpd_step_params_t* p, void* stre
  * out_host = {sum of lengths, edge count}; synchronises */
 int ngpd_session_mean_edge_length(ngpd_session_t* s, int k, double* out_host, void* stream);
 /* per-kernel device time, measured with CUDA events on the launching stream while profiling is on.
- * Categories: 0 kNN, 1 NVT+smoothing, 2 NVT+labels, 3 flat-step scalars, 4 class updates.
- * get_profile returns and clears the totals (ms_out[5], launches_out[5]); it waits for the recorded events. */
+ * Categories: 0 kNN, 1 NVT+smoothing, 2 NVT+labels, 3 flat-step scalars, 4 class updates, 5 halo refreshes + cross-rank
+ * scalars (slabs; includes the time spent waiting for the peers).
+ * get_profile returns and clears the totals (ms_out[6], launches_out[6]); it waits for the recorded events. */
 int ngpd_session_set_profiling(ngpd_session_t* s, int on);
 int ngpd_session_get_profile(ngpd_session_t* s, double* ms_out, int32_t* launches_out);
 /* kNN of the session.  The index is frozen and only the queries move, so every search also stores 2k candidates, the
@@ -220,6 +227,39 @@ int ngpd_session_export_rows(ngpd_session_t* s, int which, const int32_t* rows, 
 int ngpd_session_export_rows_peers(ngpd_session_t* s, int which, const int32_t* rows, int64_t m, const int64_t* seg,
                                    const uint64_t* peer_base, int world, void* stream);
 int ngpd_session_import_rows(ngpd_session_t* s, int which, const int32_t* rows, int64_t m, const float* in4, void* stream);
+
+/* ---- Morton slabs on several GPUs (new work, the reference is single-process).  One session per rank over its
+ * owned rows + halo copies (ngpd_session_set_owned).  Halo VALUES travel by peer stores: every rank owns one block of
+ * symmetric memory (ngpd_slab_symm_bytes, zero-filled, the same size on every rank, mapped into all peers -- e.g. torch
+ * symmetric memory over NVLink / NVSwitch) and the kernels of a refresh write the rows straight into the peers' blocks,
+ * signal with a release store and wait with acquire loads: no NCCL call, no host round trip.  The cloud-wide scalars of
+ * flat_step (Denoiser.py:106-107) are reduced through the same block, summed in rank order (identical bits on every rank).
+ * Every rank must issue the same sequence of refresh / allreduce / step_slab calls. */
+typedef struct ngpd_slab_wiring {
+    int32_t world, rank;
+    int64_t n_send, n_recv, cap;     /* cap = rows per receive buffer (>= n_recv of every rank) */
+    const int32_t* send_rows;        /* device, n_send: tree positions of the owned rows peers hold copies of, grouped by destination rank */
+    const int32_t* recv_rows;        /* device, n_recv: tree positions of this rank's halo rows, grouped by source rank, in arrival order */
+    const int64_t* send_seg_host;    /* world + 1: rows [seg[q], seg[q+1]) of send_rows go to rank q */
+    const int64_t* first_row_host;   /* world: row of rank q's receive buffer where this rank's block starts */
+    const uint64_t* symm_base_host;  /* world: address of rank q's symmetric block in this process */
+} ngpd_slab_wiring_t;
+int64_t ngpd_slab_symm_bytes(int world, int64_t cap);
+/* send_rows / recv_rows must stay alive while the wiring is set; NULL wiring clears it */
+int ngpd_session_set_slab(ngpd_session_t* s, const ngpd_slab_wiring_t* w, void* stream);
+int ngpd_session_slab_refresh(ngpd_session_t* s, int which, void* stream);      /* which: 0 positions, 1 normals, 2 smoothed normals */
+int ngpd_session_slab_allreduce(ngpd_session_t* s, int mode, void* stream);     /* 0: buffer 3 <- sum, 1: buffer 4 [3] <- max */
+/* ngpd_session_step with the halo refreshes and cross-rank scalars in between, driven from C (one call per iteration) */
+int ngpd_session_step_slab(ngpd_session_t* s, const ngpd_step_params_t* p, void* stream);
+/* largest (k-th neighbour distance + distance of the query from its tree position) any owned row has shown: the slab's
+ * searches equal the whole cloud's iff it is below the halo width.  Synchronises. */
+int ngpd_session_halo_need(ngpd_session_t* s, int reset, float* out_host, void* stream);
+/* order- and partition-independent digest of the owned rows: out11_host = {hash(id, position bits), hash(id, normal bits),
+ * sum x, sum y, sum z (int64, units of 2^-24), sum |n| (same units), label counts 0 / 1 / 2 / other, rows}.  global_ids
+ * (nullable device int64 [n]): id of the session's i-th point in the whole cloud.  Synchronises. */
+int ngpd_session_checksum(ngpd_session_t* s, const int64_t* global_ids, uint64_t* out11_host, void* stream);
+/* positions a clamped run measures its displacement from (ngpd_step_params.clamp_radius); NULL drops them */
+int ngpd_session_set_original(ngpd_session_t* s, const float* pos, void* stream);
 
 /* End-to-end entry points with HOST buffers (the path the e2e measurement times): copy this step's positions and
  * normals in, run `iterations` steps, copy positions / normals / labels back.  Synchronous. */

@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("NGPD_LIBRARY") or os.path.join(_HERE, "libngpd.so")  
 c_i64, c_i32, c_f32, c_vp = ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_void_p
 
 KNN_SKIP_SELF, KNN_QUERY_IS_TREE, KNN_COHERENT, KNN_EXACT_ONLY = 1, 2, 4, 8
+STEP_SNAPSHOT_CLASSES = 1
 STEP_FLAT, STEP_EDGE, STEP_FEATURE, STEP_CORNER, STEP_NONE = 0, 1, 2, 3, -1
 
 
@@ -24,7 +25,14 @@ class GridInfo(ctypes.Structure):
 
 class StepParams(ctypes.Structure):
     _fields_ = [("k_feature", c_i32), ("k_update", c_i32), ("x_thresh", c_f32), ("tau", c_f32), ("damp", c_f32),
-                ("scale", c_f32), ("strategy", c_i32 * 3), ("alpha", c_f32 * 3), ("dmax", c_f32)]
+                ("scale", c_f32), ("strategy", c_i32 * 3), ("alpha", c_f32 * 3), ("dmax", c_f32), ("flags", c_i32),
+                ("clamp_radius", c_f32)]
+
+
+class SlabWiring(ctypes.Structure):
+    _fields_ = [("world", c_i32), ("rank", c_i32), ("n_send", c_i64), ("n_recv", c_i64), ("cap", c_i64), ("send_rows", c_vp),
+                ("recv_rows", c_vp), ("send_seg_host", ctypes.POINTER(c_i64)), ("first_row_host", ctypes.POINTER(c_i64)),
+                ("symm_base_host", ctypes.POINTER(ctypes.c_uint64))]
 
 
 # every symbol declared in include/ngpd.h, with its ctypes signature
@@ -72,6 +80,14 @@ SIGNATURES = {
     "ngpd_session_export_rows": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_i64, c_vp, c_vp]),
     "ngpd_session_export_rows_peers": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_i64, c_vp, c_vp, ctypes.c_int, c_vp]),
     "ngpd_session_import_rows": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_i64, c_vp, c_vp]),
+    "ngpd_slab_symm_bytes": (c_i64, [ctypes.c_int, c_i64]),
+    "ngpd_session_set_slab": (ctypes.c_int, [c_vp, ctypes.POINTER(SlabWiring), c_vp]),
+    "ngpd_session_slab_refresh": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp]),
+    "ngpd_session_slab_allreduce": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp]),
+    "ngpd_session_step_slab": (ctypes.c_int, [c_vp, ctypes.POINTER(StepParams), c_vp]),
+    "ngpd_session_halo_need": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.POINTER(c_f32), c_vp]),
+    "ngpd_session_checksum": (ctypes.c_int, [c_vp, c_vp, ctypes.POINTER(ctypes.c_uint64), c_vp]),
+    "ngpd_session_set_original": (ctypes.c_int, [c_vp, c_vp, c_vp]),
     "ngpd_session_run_host": (ctypes.c_int, [c_vp, ctypes.POINTER(StepParams), ctypes.c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ngpd_denoise_host": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, ctypes.POINTER(StepParams), ctypes.c_int, c_vp, c_vp, c_vp]),
 }
@@ -290,16 +306,42 @@ class Session:
             check(load().ngpd_session_mean_edge_length(self._h, k, out, stream()), "ngpd_session_mean_edge_length")
         return out[0], out[1]
 
-    PROFILE_NAMES = ("knn", "nvt_smooth", "nvt_classify", "flat_scalars", "update")
+    PROFILE_NAMES = ("knn", "nvt_smooth", "nvt_classify", "flat_scalars", "update", "halo")
 
     def set_profiling(self, on: bool):
         check(load().ngpd_session_set_profiling(self._h, int(on)), "ngpd_session_set_profiling")
 
     def get_profile(self) -> dict:
-        ms = (ctypes.c_double * 5)()
-        cnt = (c_i32 * 5)()
+        ms = (ctypes.c_double * len(self.PROFILE_NAMES))()
+        cnt = (c_i32 * len(self.PROFILE_NAMES))()
         check(load().ngpd_session_get_profile(self._h, ms, cnt), "ngpd_session_get_profile")
         return {name: (ms[i], cnt[i]) for i, name in enumerate(self.PROFILE_NAMES)}
+
+    CHECKSUM_FIELDS = ("pos_hash", "nrm_hash", "sum_x_q24", "sum_y_q24", "sum_z_q24", "sum_norm_q24", "label0", "label1", "label2",
+                       "label_other", "rows")
+
+    def checksum(self, global_ids: torch.Tensor | None = None) -> list[int]:
+        """Order- and partition-independent digest of the owned rows (integers; ngpd_session_checksum).  Digests of
+        disjoint slabs add up (mod 2^64) to the digest of the whole cloud."""
+        out = (ctypes.c_uint64 * len(self.CHECKSUM_FIELDS))()
+        if global_ids is not None:
+            global_ids = dev(global_ids, torch.int64, "global_ids")
+            assert global_ids.numel() == self.n
+        with torch.cuda.device(self.device):
+            check(load().ngpd_session_checksum(self._h, ptr(global_ids), out, stream()), "ngpd_session_checksum")
+        return [int(v) for v in out]
+
+    def halo_need(self, reset: bool = False) -> float:
+        out = c_f32()
+        with torch.cuda.device(self.device):
+            check(load().ngpd_session_halo_need(self._h, int(reset), ctypes.byref(out), stream()), "ngpd_session_halo_need")
+        return float(out.value)
+
+    def set_original(self, pos: torch.Tensor | None):
+        """positions the displacement clamp (StepParams.clamp_radius) is measured from, original point order"""
+        pos = dev(pos, torch.float32, "pos") if pos is not None else None
+        with torch.cuda.device(self.device):
+            check(load().ngpd_session_set_original(self._h, ptr(pos), stream()), "ngpd_session_set_original")
 
     def set_knn_mode(self, mode):
         """0 / False: all tiers (default); 1 / True: exact shell search only; 2: streaming tiers without re-ranking"""
@@ -337,7 +379,8 @@ class Session:
 
 
 def make_params(k_feature=16, k_update=8, rho=None, tau=0.3, damp=3.0, scale=0.2,
-                strategy=(STEP_FLAT, STEP_EDGE, STEP_FEATURE), alpha=(1.0, 0.2, 1.0), dmax=0.0) -> StepParams:
+                strategy=(STEP_FLAT, STEP_EDGE, STEP_FEATURE), alpha=(1.0, 0.2, 1.0), dmax=0.0, flags=0,
+                clamp_radius=0.0) -> StepParams:
     import math
 
     p = StepParams()
@@ -348,4 +391,5 @@ def make_params(k_feature=16, k_update=8, rho=None, tau=0.3, damp=3.0, scale=0.2
         p.strategy[i] = int(strategy[i])
         p.alpha[i] = float(alpha[i])
     p.dmax = float(dmax)
+    p.flags, p.clamp_radius = int(flags), float(clamp_radius)
     return p

@@ -15,7 +15,30 @@
 #include "point_math.cuh"
 #include "../../include/ngpd.h"
 
-#define NGPD_PROF_CATEGORIES 5   // 0 knn, 1 nvt+smooth, 2 nvt+classify, 3 flat scalars, 4 update
+#define NGPD_PROF_CATEGORIES 6   // 0 knn, 1 nvt+smooth, 2 nvt+classify, 3 flat scalars, 4 update, 5 halo exchange + cross-rank scalars (multi-GPU)
+
+namespace ngpd {
+// What the cross-rank kernels need, by value (world <= NGPD_SLAB_MAX_WORLD).  Every rank owns one block of symmetric
+// memory with the same layout, mapped into all peers (NVLink / NVSwitch):
+//   halo[2][cap] float4   receive buffers of the halo rows, used alternately (parity of the round)
+//   scal[2][world][4] f64 one slot per source rank for the cloud-wide scalars of flat_step
+//   flag[world] u64       round number last signalled by each source rank
+constexpr int SLAB_MAX_WORLD = 16;
+struct SlabDev {
+    int world, rank;
+    long long cap;
+    long long seg[SLAB_MAX_WORLD + 1];            // rows [seg[q], seg[q+1]) of the send list go to rank q
+    long long first_row[SLAB_MAX_WORLD];          // ... and land at this row of rank q's receive buffer
+    unsigned long long base[SLAB_MAX_WORLD];      // address of rank q's block in this process
+    __host__ __device__ float4* halo(int q, int parity) const { return reinterpret_cast<float4*>(base[q]) + (long long)parity * cap; }
+    __host__ __device__ double* scal(int q, int parity) const {
+        return reinterpret_cast<double*>(base[q] + 2ull * (unsigned long long)cap * 16ull) + (long long)parity * world * 4;
+    }
+    __host__ __device__ unsigned long long* flag(int q) const {
+        return reinterpret_cast<unsigned long long*>(base[q] + 2ull * (unsigned long long)cap * 16ull + 2ull * world * 32ull);
+    }
+};
+}
 
 struct ngpd_session {
     ngpd_grid* grid = nullptr;
@@ -48,6 +71,7 @@ struct ngpd_session {
     int32_t* inv = nullptr;   // original index -> tree position (built on the first read-back)
     bool lists_ready = false; // cls[] matches label[]
     float* cd = nullptr;      // centre xyz, delta
+    float4* orig = nullptr;   // positions a clamped run measures its displacement from (ngpd_session_set_original), tree order
     int launches = 0;
     int knn_launches = 0;     // kernels of the last kNN pass
     // staging for the host-buffer entry point (packed [n,3] positions, normals, labels), allocated on first use
@@ -68,8 +92,16 @@ struct ngpd_session {
     bool profiling = false;
     std::vector<cudaEvent_t> ev;      // pairs
     std::vector<int> ev_cat;
-    double prof_ms[NGPD_PROF_CATEGORIES] = {0, 0, 0, 0, 0};
-    int prof_n[NGPD_PROF_CATEGORIES] = {0, 0, 0, 0, 0};
+    double prof_ms[NGPD_PROF_CATEGORIES] = {0, 0, 0, 0, 0, 0};
+    int prof_n[NGPD_PROF_CATEGORIES] = {0, 0, 0, 0, 0, 0};
+    // Morton-slab wiring (ngpd_session_set_slab): halo rows travel by peer stores into symmetric memory, see the slab section
+    ngpd::SlabDev* slab = nullptr;     // host copy of what the exchange kernels get by value
+    const int32_t* slab_send_rows = nullptr;   // caller-owned device arrays
+    const int32_t* slab_recv_rows = nullptr;
+    int64_t slab_n_send = 0, slab_n_recv = 0;
+    unsigned long long slab_epoch = 0;         // one per cross-rank round, the same sequence on every rank
+    unsigned* slab_done = nullptr;             // block counter of the export kernel
+    float* halo_need = nullptr;                // max over the owned rows of (k-th neighbour distance + distance moved from the tree position)
 };
 
 namespace ngpd {
@@ -86,20 +118,39 @@ struct ProfScope {
 
 namespace ngpd {
 
+// Slabs only (need != nullptr): running maximum over the owned rows of  d_k + |query - its own tree position|.  Every tree
+// point within the halo width of an owned point's TREE position is resident, so a row whose value stays below that width
+// has seen every candidate the whole cloud would offer (partition.py checks it after the run).  All lanes must call.
+__device__ __forceinline__ void note_halo_need(float* __restrict__ need, bool active, double dk2, float4 q, const float4* __restrict__ tree_pts, int64_t s) {
+    float v = 0.0f;
+    if (active) {
+        const float4 t = __ldg(tree_pts + s);
+        const float dx = q.x - t.x, dy = q.y - t.y, dz = q.z - t.z;
+        v = (float)sqrt(dk2) * 1.000001f + sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx))) * 1.000001f;
+        if (!(v == v)) v = 3.0e38f;
+    }
+    const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(v));
+    if ((threadIdx.x & 31) == 0 && m > *reinterpret_cast<volatile unsigned*>(need)) atomicMax(reinterpret_cast<unsigned*>(need), m);
+}
+
 template <int K>
 __global__ void __launch_bounds__(128) session_knn_kernel(GridView g, const float4* __restrict__ pos, const uint8_t* __restrict__ owned,
-                                                          int64_t n, int k, int32_t* __restrict__ idx) {
+                                                          int64_t n, int k, int32_t* __restrict__ idx, float* __restrict__ need) {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    if (owned && !owned[s]) return;
-    float4 q = __ldg(pos + s);
-    TopK<K> top;
-    top.init();
-    knn_search<K>(top, g, (double)q.x, (double)q.y, (double)q.z, -1);
-    int32_t* row = idx + s * k;
+    const bool active = s < n && (!owned || owned[s]);
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    double dk2 = 0.0;
+    if (active) {
+        q = __ldg(pos + s);
+        TopK<K> top;
+        top.init();
+        knn_search<K>(top, g, (double)q.x, (double)q.y, (double)q.z, -1);
+        int32_t* row = idx + s * k;
 #pragma unroll
-    for (int a = 0; a < K; ++a)
-        if (a < k) row[a] = top.id[a] >= 0 ? top.id[a] : (int32_t)s;   // fewer than k tree points: pad with self
+        for (int a = 0; a < K; ++a)
+            if (a < k) { row[a] = top.id[a] >= 0 ? top.id[a] : (int32_t)s; if (a == k - 1 && top.id[a] >= 0) dk2 = top.d[a]; }   // fewer than k tree points: pad with self
+    }
+    if (need) note_halo_need(need, active, dk2, q, g.pts, active ? s : 0);
 }
 
 // What a search leaves behind for the re-ranking tier (knn_stream.cuh, "tier 0"): per row the position it was asked
@@ -107,6 +158,7 @@ __global__ void __launch_bounds__(128) session_knn_kernel(GridView g, const floa
 struct KnnTrack {
     int32_t* cand;      // [n * KT]
     float4* anchor;     // [n]
+    float* need;        // nullable: note_halo_need's slot (slabs only)
 };
 
 template <int K, int KT>
@@ -144,6 +196,7 @@ __global__ void __launch_bounds__(128, K <= 16 ? 5 : 4) session_knn_rerank_kerne
     // (rows that are not this rank's, or past the end, re-rank whatever their column holds -- zeros unless searched before -- and drop the result)
     bool ok = ks_rerank<K>(top, g, KsRowShared<2 * K>{tile, (int)threadIdx.x}, an, q.x, q.y, q.z, ex);
     ok = ok && active && an.w > 0.0f;
+    if (tr.need) note_halo_need(tr.need, ok, ex[K - 1], q, g.pts, s);
     if (k == K) {
         // rows out through the tile as well: the block's 128 rows are one contiguous 128*K*4-byte piece of the table, written
         // with coalesced 16-byte stores (a lane storing its own 64-byte row touches a cache line per two lanes)
@@ -179,6 +232,7 @@ __device__ __forceinline__ void session_knn_body(KsShared<R>& sm, const GridView
     constexpr int KF = ks_kf(K, KT);
     double ex[KF];
     ks_finalize<KF, KT>(top, g.pts, q.x, q.y, q.z, ex);
+    if (tr.need) note_halo_need(tr.need, active && ok, ex[K - 1], q, g.pts, s);
     if (active && ok) {
         session_write_row<K, KT>(s, k, top.id, idx);
         if (KT > K) {
@@ -229,31 +283,37 @@ template <int K, int KT>
 __global__ void __launch_bounds__(128) session_knn_fix_kernel(GridView g, const float4* __restrict__ pos, int k, int32_t* __restrict__ idx, KnnTrack tr,
                                                               const int32_t* __restrict__ fix_list, const int32_t* __restrict__ fix_count) {
     const int cnt = *fix_count;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
-        const int64_t s = fix_list[i];
+    for (int base = blockIdx.x * blockDim.x; base < cnt; base += gridDim.x * blockDim.x) {
+        const int i = base + threadIdx.x;
+        const bool active = i < cnt;
+        const int64_t s = active ? fix_list[i] : 0;
         const float4 q = __ldg(pos + s);
+        double dk2 = 0.0;
         // A 64-entry fp64 list lives in local memory (measured: 1.8 ms for a handful of rows) and a 48-entry one at 255
         // registers is not much better (1.3 ms for 100 rows): with K = 32 only the row itself is searched here and nothing is
         // stored for tier 0 (radius 0 = the row goes through the search tiers again next time; ~0.04 % of the rows, the ones
         // in regions dense enough to overflow the 5x5x5 tier's range slots).
         constexpr int KS = (KT > 32 && K <= 32) ? K : KT;
-        TopK<KS> top;
-        top.init();
-        knn_search<KS>(top, g, (double)q.x, (double)q.y, (double)q.z, -1);
-        int32_t* row = idx + s * k;
+        if (active) {
+            TopK<KS> top;
+            top.init();
+            knn_search<KS>(top, g, (double)q.x, (double)q.y, (double)q.z, -1);
+            int32_t* row = idx + s * k;
 #pragma unroll
-        for (int a = 0; a < K; ++a)
-            if (a < k) row[a] = top.id[a] >= 0 ? top.id[a] : (int32_t)s;   // fewer than k tree points: pad with self
-        if constexpr (KT > K && KS < KT) {
-            tr.anchor[s] = make_float4(q.x, q.y, q.z, 0.0f);
-        } else if constexpr (KT > K) {
-            int4* crow = reinterpret_cast<int4*>(tr.cand + s * KT);
+            for (int a = 0; a < K; ++a)
+                if (a < k) { row[a] = top.id[a] >= 0 ? top.id[a] : (int32_t)s; if (a == k - 1 && top.id[a] >= 0) dk2 = top.d[a]; }   // fewer than k tree points: pad with self
+            if constexpr (KT > K && KS < KT) {
+                tr.anchor[s] = make_float4(q.x, q.y, q.z, 0.0f);
+            } else if constexpr (KT > K) {
+                int4* crow = reinterpret_cast<int4*>(tr.cand + s * KT);
 #pragma unroll
-            for (int a = 0; a < KT / 4; ++a) crow[a] = make_int4(top.id[4 * a], top.id[4 * a + 1], top.id[4 * a + 2], top.id[4 * a + 3]);
-            // a full list: nothing outside it is closer than its last entry; a short one holds the whole tree
-            const float rlim = top.id[KT - 1] >= 0 ? __double2float_rd(sqrt(top.d[KT - 1]) * (1.0 - 1e-7)) : 3.0e38f;
-            tr.anchor[s] = make_float4(q.x, q.y, q.z, top.id[K - 1] >= 0 ? rlim : 0.0f);
+                for (int a = 0; a < KT / 4; ++a) crow[a] = make_int4(top.id[4 * a], top.id[4 * a + 1], top.id[4 * a + 2], top.id[4 * a + 3]);
+                // a full list: nothing outside it is closer than its last entry; a short one holds the whole tree
+                const float rlim = top.id[KT - 1] >= 0 ? __double2float_rd(sqrt(top.d[KT - 1]) * (1.0 - 1e-7)) : 3.0e38f;
+                tr.anchor[s] = make_float4(q.x, q.y, q.z, top.id[K - 1] >= 0 ? rlim : 0.0f);
+            }
         }
+        if (tr.need) note_halo_need(tr.need, active, dk2, q, g.pts, s);
     }
 }
 
@@ -492,17 +552,28 @@ __device__ __forceinline__ V3 session_move_point(int kind, const Quad4& pos, con
     }
 }
 
+// the notebook's displacement clamp (PostProcessing.ipynb#c9: mask = (temp_pos - original_pos).norm(dim=1) < d;
+// pos[mask] = temp_pos[mask]): a moved point is kept only while it stays within clamp_r of its original position
+__device__ __forceinline__ V3 clamp_to_original(V3 moved, V3 old, const float4* __restrict__ orig, int64_t s, float clamp_r) {
+    if (!orig) return moved;
+    const float4 o = __ldg(orig + s);
+    return norm3_fma(moved - v3(o.x, o.y, o.z)) < clamp_r ? moved : old;
+}
+
 // one class: members move, everybody else is copied through to the other buffer (snapshot semantics)
 template <int KU>
 __global__ void __launch_bounds__(128, 10) session_update_kernel(int kind, int key, Quad4 pos, Quad4 fn, const float4* __restrict__ edge,
                                                              const uint8_t* __restrict__ label, const uint8_t* __restrict__ owned,
                                                              const int32_t* __restrict__ idx, int64_t n, int k, int ku, float alpha, float dmax,
-                                                             const float* __restrict__ cd, float4* __restrict__ out) {
+                                                             const float* __restrict__ cd, const float4* __restrict__ orig, float clamp_r,
+                                                             float4* __restrict__ out) {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     V3 p = pos(s);
-    if (label[s] == key && (!owned || owned[s]) && kind >= NGPD_STEP_FLAT && kind <= NGPD_STEP_CORNER)
-        p = session_move_point<KU>(kind, pos, fn, edge, s, idx + s * k, ku, cd, alpha, dmax);
+    if (label[s] == key && (!owned || owned[s]) && kind >= NGPD_STEP_FLAT && kind <= NGPD_STEP_CORNER) {
+        const V3 q = session_move_point<KU>(kind, pos, fn, edge, s, idx + s * k, ku, cd, alpha, dmax);
+        p = clamp_to_original(q, p, orig, s, clamp_r);
+    }
     out[s] = make_float4(p.x, p.y, p.z, 0.0f);
 }
 
@@ -512,12 +583,16 @@ template <int KU>
 __global__ void __launch_bounds__(128) session_update_rows_kernel(int kind, Quad4 pos, Quad4 fn, const float4* __restrict__ edge,
                                                                   const int32_t* __restrict__ list, const int32_t* __restrict__ count,
                                                                   const int32_t* __restrict__ idx, int k, int ku, float alpha, float dmax,
-                                                                  const float* __restrict__ cd, float4* __restrict__ moved) {
+                                                                  const float* __restrict__ cd, const float4* __restrict__ orig, float clamp_r,
+                                                                  float4* __restrict__ moved, bool scatter) {
+    // scatter == false: moved[i] = new position of the i-th listed row (applied afterwards, in place);
+    // scatter == true (every class moves from the same snapshot): `moved` is the other position buffer, written at the row itself
     const int cnt = *count;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
         const int64_t s = list[i];
-        const V3 p = session_move_point<KU>(kind, pos, fn, edge, s, idx + s * k, ku, cd, alpha, dmax);
-        moved[i] = make_float4(p.x, p.y, p.z, 0.0f);
+        const V3 q = session_move_point<KU>(kind, pos, fn, edge, s, idx + s * k, ku, cd, alpha, dmax);
+        const V3 p = clamp_to_original(q, pos(s), orig, s, clamp_r);
+        moved[scatter ? s : (int64_t)i] = make_float4(p.x, p.y, p.z, 0.0f);
     }
 }
 __global__ void __launch_bounds__(256) session_apply_rows_kernel(const int32_t* __restrict__ list, const int32_t* __restrict__ count,
@@ -601,6 +676,122 @@ __global__ void __launch_bounds__(256) session_import_kernel(float4* __restrict_
     if (i < m) dst[rows[i]] = in[i];
 }
 
+
+// ---- Morton slabs: halo rows by peer stores, cloud-wide scalars through the same symmetric block -------------------------
+// One cross-rank ROUND = everybody writes into its peers' memory, signals the round number to every peer (release), and waits
+// until every peer's number has arrived (acquire) before it reads what the peers wrote.  No NCCL call and no host round trip:
+// a halo refresh is two kernels (gather + push, wait + scatter), a scalar all-reduce is one.  Buffers alternate with the
+// parity of the round: a rank can only be one round ahead of a peer (it needs that peer's signal to get further), so the
+// buffers of round t are not written again before every reader of round t has signalled round t + 1, i.e. is done reading.
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// rows of this rank that peers hold as halo copies: gathered and stored straight into the owners' receive buffers; the block
+// that finishes last tells every peer that this rank's rows of round `epoch` are in place
+__global__ void __launch_bounds__(256) slab_push_kernel(SlabDev d, const float4* __restrict__ src, const int32_t* __restrict__ rows, int64_t m,
+                                                        int parity, unsigned long long epoch, unsigned* __restrict__ done) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+        int q = 0;
+        while (q + 1 < d.world && i >= d.seg[q + 1]) ++q;
+        d.halo(q, parity)[d.first_row[q] + (i - d.seg[q])] = src[rows[i]];
+    }
+    __threadfence_system();
+    __shared__ bool last;
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(done, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (last) {
+        __threadfence_system();
+        if (threadIdx.x < d.world && (int)threadIdx.x != d.rank) st_release_sys(d.flag(threadIdx.x) + d.rank, epoch);
+        if (threadIdx.x == 0) *done = 0;
+    }
+}
+// the other half: wait for every peer's rows of round `epoch`, then scatter this rank's receive buffer into the halo rows
+__global__ void __launch_bounds__(256) slab_pull_kernel(SlabDev d, float4* __restrict__ dst, const int32_t* __restrict__ rows, int64_t m,
+                                                        int parity, unsigned long long epoch) {
+    if (threadIdx.x < d.world && (int)threadIdx.x != d.rank) {
+        const unsigned long long* f = d.flag(d.rank) + threadIdx.x;
+        while (ld_acquire_sys(f) < epoch) __nanosleep(64);
+    }
+    __syncthreads();
+    const float4* in = d.halo(d.rank, parity);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x)
+        dst[rows[i]] = __ldcv(in + i);
+}
+// flat_step's cloud-wide scalars across ranks (Denoiser.py:106-107).  mode 0: acc[0..3] <- sum over ranks of acc[0..3] (added in
+// rank order on every rank: identical bits everywhere); mode 1: cd[3] <- max over ranks.  One warp.
+__global__ void __launch_bounds__(32) slab_allreduce_kernel(SlabDev d, double* __restrict__ acc, float* __restrict__ cd, int mode, int parity,
+                                                            unsigned long long epoch) {
+    const int q = threadIdx.x;
+    double v[4];
+    if (mode == 0) { v[0] = acc[0]; v[1] = acc[1]; v[2] = acc[2]; v[3] = acc[3]; }
+    else { v[0] = (double)cd[3]; v[1] = v[2] = v[3] = 0.0; }
+    if (q < d.world) {
+        double* slot = d.scal(q, parity) + d.rank * 4;
+        slot[0] = v[0]; slot[1] = v[1]; slot[2] = v[2]; slot[3] = v[3];
+        __threadfence_system();
+        if (q != d.rank) {
+            st_release_sys(d.flag(q) + d.rank, epoch);
+            const unsigned long long* f = d.flag(d.rank) + q;
+            while (ld_acquire_sys(f) < epoch) __nanosleep(32);
+        }
+    }
+    __syncwarp();
+    const volatile double* mine = d.scal(d.rank, parity);
+    if (mode == 0) {
+        if (q < 4) { double t = 0.0; for (int r = 0; r < d.world; ++r) t += mine[r * 4 + q]; acc[q] = t; }
+    } else if (q == 0) {
+        double t = mine[0];
+        for (int r = 1; r < d.world; ++r) t = fmax(t, mine[r * 4]);
+        cd[3] = (float)t;
+    }
+}
+
+// ---- order-independent checksum of the owned rows (bench.py: the lines of different GPU counts must agree bit for bit) -------
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {   // splitmix64 finaliser
+    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull; x ^= x >> 27; x *= 0x94d049bb133111ebull; x ^= x >> 31;
+    return x;
+}
+constexpr int CHECKSUM_WORDS = 11;
+// out: 0 hash of (global id, position bits), 1 hash of (global id, normal bits), 2-4 sum of x, y, z in units of 2^-24 (int64),
+// 5 sum of |n| in units of 2^-24, 6-9 label histogram (0, 1, 2, other), 10 rows counted.  All integer sums: any order, any partition.
+__global__ void __launch_bounds__(256) session_checksum_kernel(const float4* __restrict__ tree_pts, const float4* __restrict__ pos,
+                                                               const float4* __restrict__ nrm, const uint8_t* __restrict__ label,
+                                                               const uint8_t* __restrict__ owned, const int64_t* __restrict__ gids, int64_t n,
+                                                               unsigned long long* __restrict__ out) {
+    unsigned long long a[CHECKSUM_WORDS];
+#pragma unroll
+    for (int c = 0; c < CHECKSUM_WORDS; ++c) a[c] = 0;
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += (int64_t)gridDim.x * blockDim.x) {
+        if (owned && !owned[s]) continue;
+        const int64_t o = (int64_t)__float_as_int(__ldg(&tree_pts[s].w));
+        const unsigned long long g = (unsigned long long)(gids ? gids[o] : o);
+        const float4 p = pos[s], v = nrm[s];
+        a[0] += mix64(g * 0x9e3779b97f4a7c15ull ^ ((unsigned long long)__float_as_uint(p.x) | ((unsigned long long)__float_as_uint(p.y) << 32))) +
+                mix64(g * 0xc2b2ae3d27d4eb4full ^ (unsigned long long)__float_as_uint(p.z));
+        a[1] += mix64(g * 0x9e3779b97f4a7c15ull ^ ((unsigned long long)__float_as_uint(v.x) | ((unsigned long long)__float_as_uint(v.y) << 32))) +
+                mix64(g * 0xc2b2ae3d27d4eb4full ^ (unsigned long long)__float_as_uint(v.z));
+        a[2] += (unsigned long long)llrint((double)p.x * 16777216.0);
+        a[3] += (unsigned long long)llrint((double)p.y * 16777216.0);
+        a[4] += (unsigned long long)llrint((double)p.z * 16777216.0);
+        a[5] += (unsigned long long)llrint(sqrt((double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z) * 16777216.0);
+        const int l = label[s];
+        a[6] += l == 0; a[7] += l == 1; a[8] += l == 2; a[9] += l > 2;
+        a[10] += 1;
+    }
+#pragma unroll
+    for (int c = 0; c < CHECKSUM_WORDS; ++c) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a[c] += __shfl_xor_sync(0xffffffffu, a[c], o);
+        if ((threadIdx.x & 31) == 0 && a[c]) atomicAdd(out + c, a[c]);
+    }
+}
+
 static inline unsigned strided(int64_t n, int threads) {
     int64_t b = cdiv(n, threads), cap = (int64_t)num_sms() * 8;
     return (unsigned)(b < cap ? (b > 0 ? b : 1) : cap);
@@ -632,7 +823,7 @@ static void run_knn_tiers(ngpd_session* S, int k, int32_t* idx, cudaStream_t st,
     const GridView& g = S->grid->v;
     const float4* p = S->pos[S->cur];
     KnnLists L(S);
-    KnnTrack tr{S->cand, S->anchor};
+    KnnTrack tr{S->cand, S->anchor, S->owned ? S->halo_need : nullptr};
     uint8_t* late = S->overlap_tail ? S->late : nullptr;
     if (todo)
         session_knn_fast_kernel<K, KT><<<stride_blocks(S->n, KsCfg<1>::THREADS, 16), KsCfg<1>::THREADS, 0, st>>>(
@@ -678,7 +869,7 @@ static int run_knn_fast(ngpd_session* S, int k, int32_t* idx, cudaStream_t st, b
     if constexpr (CAN_TRACK) {
         if (rerank_ok && S->cand_k == K) {
             // tier 0 first; what it cannot answer is searched (tracked: re-anchored, untracked: just answered)
-            session_knn_rerank_kernel<K><<<(unsigned)cdiv(S->n, 128), 128, 0, st>>>(g, S->pos[S->cur], S->owned, S->n, k, idx, KnnTrack{S->cand, S->anchor},
+            session_knn_rerank_kernel<K><<<(unsigned)cdiv(S->n, 128), 128, 0, st>>>(g, S->pos[S->cur], S->owned, S->n, k, idx, KnnTrack{S->cand, S->anchor, S->owned ? S->halo_need : nullptr},
                                                                                 L.list[0], L.cnt[0]);
             if (track) run_knn_tiers<K, 2 * K>(S, k, idx, st, true);
             else run_knn_tiers<K, K>(S, k, idx, st, true);
@@ -706,11 +897,11 @@ static int run_knn(ngpd_session* S, int k, int32_t* idx, cudaStream_t st, bool t
         else if (kt <= 32) rc = run_knn_fast<32>(S, k, idx, st, track);
         else rc = run_knn_fast<64>(S, k, idx, st, track);
     }
-    else if (k <= 4) session_knn_kernel<4><<<b, 128, 0, st>>>(g, p, S->owned, S->n, k, idx);
-    else if (k <= 8) session_knn_kernel<8><<<b, 128, 0, st>>>(g, p, S->owned, S->n, k, idx);
-    else if (k <= 16) session_knn_kernel<16><<<b, 128, 0, st>>>(g, p, S->owned, S->n, k, idx);
-    else if (k <= 32) session_knn_kernel<32><<<b, 128, 0, st>>>(g, p, S->owned, S->n, k, idx);
-    else session_knn_kernel<64><<<b, 128, 0, st>>>(g, p, S->owned, S->n, k, idx);
+    else if (k <= 4) session_knn_kernel<4><<<b, 128, 0, st>>>(g, p, S->owned, S->n, k, idx, S->owned ? S->halo_need : nullptr);
+    else if (k <= 8) session_knn_kernel<8><<<b, 128, 0, st>>>(g, p, S->owned, S->n, k, idx, S->owned ? S->halo_need : nullptr);
+    else if (k <= 16) session_knn_kernel<16><<<b, 128, 0, st>>>(g, p, S->owned, S->n, k, idx, S->owned ? S->halo_need : nullptr);
+    else if (k <= 32) session_knn_kernel<32><<<b, 128, 0, st>>>(g, p, S->owned, S->n, k, idx, S->owned ? S->halo_need : nullptr);
+    else session_knn_kernel<64><<<b, 128, 0, st>>>(g, p, S->owned, S->n, k, idx, S->owned ? S->halo_need : nullptr);
     if (rc) return rc;
     NGPD_CUDA_OK(cudaGetLastError());
     return 0;
@@ -723,11 +914,14 @@ using namespace ngpd;
 extern "C" __attribute__((visibility("default"))) int ngpd_session_destroy(ngpd_session_t* S) {
     if (!S) return 0;
     if (S->grid) ngpd_grid_destroy(S->grid);
-    void* bufs[] = {S->pos[0], S->pos[1], S->nrm, S->fn, S->edge, S->label, S->owned, S->idx, S->acc, S->cd, S->fix, S->cand, S->anchor, S->part, S->red2, S->cls, S->inv, S->stage_pos, S->stage_nrm, S->stage_lab};
+    void* bufs[] = {S->pos[0], S->pos[1], S->nrm, S->fn, S->edge, S->label, S->owned, S->idx, S->acc, S->cd, S->fix, S->cand, S->anchor, S->part, S->red2, S->cls, S->inv, S->stage_pos, S->stage_nrm, S->stage_lab, S->orig};
     for (void* b : bufs) if (b) cudaFree(b);
     if (S->side) { cudaStreamDestroy(S->side); for (cudaEvent_t e : S->xfer) if (e) cudaEventDestroy(e); }
     if (S->tail) { cudaStreamDestroy(S->tail); for (cudaEvent_t e : S->tail_ev) if (e) cudaEventDestroy(e); }
     if (S->late) cudaFree(S->late);
+    if (S->slab_done) cudaFree(S->slab_done);
+    if (S->halo_need) cudaFree(S->halo_need);
+    delete S->slab;
     delete S;
     return 0;
 }
@@ -791,6 +985,10 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_set_owned(ngp
     S->lists_ready = false;
     if (!owned_tree_order) { if (S->owned) cudaFree(S->owned); S->owned = nullptr; return 0; }
     if (!S->owned) NGPD_CUDA_OK(cudaMalloc(&S->owned, (size_t)S->n));
+    if (!S->halo_need) {
+        NGPD_CUDA_OK(cudaMalloc(&S->halo_need, sizeof(float)));
+        NGPD_CUDA_OK(cudaMemsetAsync(S->halo_need, 0, sizeof(float), (cudaStream_t)stream_));
+    }
     NGPD_CUDA_OK(cudaMemcpyAsync(S->owned, owned_tree_order, (size_t)S->n, cudaMemcpyDeviceToDevice, (cudaStream_t)stream_));
     return 0;
 }
@@ -896,7 +1094,8 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_phase_feature
 extern "C" __attribute__((visibility("default"))) int ngpd_session_phase_flat_scalars(ngpd_session_t* S, const ngpd_step_params_t* p, int key, int part, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     NGPD_REQUIRE(S && p, "ngpd_session_phase_flat_scalars: NULL argument");
-    Quad4 pos{S->pos[S->cur]};
+    // (snapshot mode: classes 1 and 2 still read the positions class 0's pass started from)
+    Quad4 pos{S->pos[((p->flags & NGPD_STEP_SNAPSHOT_CLASSES) && key > 0) ? S->cur ^ 1 : S->cur]};
     ProfScope ps(S, st, 3);
     if (part == 0 && key == 0 && S->sums_ready) {
         session_partial_reduce_kernel<<<RED_BLOCKS, 256, 0, st>>>(S->part, cdiv(S->n, 128), S->red2, S->acc);
@@ -921,36 +1120,57 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_phase_update(
     cudaStream_t st = (cudaStream_t)stream_;
     NGPD_REQUIRE(S && p && key >= 0 && key < 3, "ngpd_session_phase_update: bad argument");
     int kind = p->strategy[key];
-    if (kind < 0) return 0;
+    const bool snapshot = (p->flags & NGPD_STEP_SNAPSHOT_CLASSES) != 0;
+    // snapshot mode: class 0's pass doubles as the copy of the snapshot into the other buffer, so it runs even when class 0 stays put
+    if (kind < 0 && !(snapshot && key == 0)) return 0;
+    const float4* orig = p->clamp_radius > 0.0f ? S->orig : nullptr;
+    NGPD_REQUIRE(!(p->clamp_radius > 0.0f) || S->orig, "ngpd_session_phase_update: clamp_radius needs ngpd_session_set_original first");
+    NGPD_REQUIRE(!snapshot || S->lists_ready, "ngpd_session_phase_update: the snapshot mode needs the class lists of phase_features part 1");
     ProfScope ps(S, st, 4);
     const bool fixed8 = p->k_update == 8 && S->idx_k % 4 == 0;   // rows of 8 ids, 16-byte aligned
     if (key > 0 && S->lists_ready) {
-        // minority class: its rows only, in place (the other position buffer is free and holds the moved rows in between)
+        // minority class: its rows only.  Sequential mode: in place (the other position buffer is free and holds the moved rows
+        // in between).  Snapshot mode: read the snapshot (the buffer class 0's pass read), write the rows of the current buffer.
         const int32_t *list = S->cls + (int64_t)(key - 1) * S->n, *count = S->cls + 2 * S->n + (key - 1);
+        const float4* src = S->pos[snapshot ? S->cur ^ 1 : S->cur];
+        float4* dst = S->pos[snapshot ? S->cur : S->cur ^ 1];
         if (fixed8)
-            session_update_rows_kernel<8><<<stride_blocks(S->n, 128, 16), 128, 0, st>>>(kind, Quad4{S->pos[S->cur]}, Quad4{S->fn}, S->edge, list, count, S->idx,
-                                                                                     S->idx_k, p->k_update, p->alpha[key], p->dmax, S->cd, S->pos[S->cur ^ 1]);
+            session_update_rows_kernel<8><<<stride_blocks(S->n, 128, 16), 128, 0, st>>>(kind, Quad4{src}, Quad4{S->fn}, S->edge, list, count, S->idx,
+                                                                                     S->idx_k, p->k_update, p->alpha[key], p->dmax, S->cd, orig, p->clamp_radius, dst, snapshot);
         else
-            session_update_rows_kernel<0><<<stride_blocks(S->n, 128, 16), 128, 0, st>>>(kind, Quad4{S->pos[S->cur]}, Quad4{S->fn}, S->edge, list, count, S->idx,
-                                                                                     S->idx_k, p->k_update, p->alpha[key], p->dmax, S->cd, S->pos[S->cur ^ 1]);
-        session_apply_rows_kernel<<<stride_blocks(S->n, 256, 8), 256, 0, st>>>(list, count, S->pos[S->cur ^ 1], S->pos[S->cur]);
+            session_update_rows_kernel<0><<<stride_blocks(S->n, 128, 16), 128, 0, st>>>(kind, Quad4{src}, Quad4{S->fn}, S->edge, list, count, S->idx,
+                                                                                     S->idx_k, p->k_update, p->alpha[key], p->dmax, S->cd, orig, p->clamp_radius, dst, snapshot);
+        S->launches += 1;
+        if (!snapshot) {
+            session_apply_rows_kernel<<<stride_blocks(S->n, 256, 8), 256, 0, st>>>(list, count, S->pos[S->cur ^ 1], S->pos[S->cur]);
+            S->launches += 1;
+        }
         NGPD_CUDA_OK(cudaGetLastError());
         S->sums_ready = false;
-        S->launches += 2;
         return 0;
     }
     if (fixed8)
         session_update_kernel<8><<<(unsigned)cdiv(S->n, 128), 128, 0, st>>>(kind, key, Quad4{S->pos[S->cur]}, Quad4{S->fn}, S->edge, S->label, S->owned,
                                                                             S->idx, S->n, S->idx_k, p->k_update, p->alpha[key], p->dmax, S->cd,
-                                                                            S->pos[S->cur ^ 1]);
+                                                                            orig, p->clamp_radius, S->pos[S->cur ^ 1]);
     else
         session_update_kernel<0><<<(unsigned)cdiv(S->n, 128), 128, 0, st>>>(kind, key, Quad4{S->pos[S->cur]}, Quad4{S->fn}, S->edge, S->label, S->owned,
                                                                             S->idx, S->n, S->idx_k, p->k_update, p->alpha[key], p->dmax, S->cd,
-                                                                            S->pos[S->cur ^ 1]);
+                                                                            orig, p->clamp_radius, S->pos[S->cur ^ 1]);
     NGPD_CUDA_OK(cudaGetLastError());
     S->cur ^= 1;
     S->sums_ready = false;
     S->launches += 1;
+    return 0;
+}
+
+// the positions a clamped run measures its displacement from (original point order; NULL drops them)
+extern "C" __attribute__((visibility("default"))) int ngpd_session_set_original(ngpd_session_t* S, const float* pos, void* stream_) {
+    NGPD_REQUIRE(S, "ngpd_session_set_original: NULL session");
+    if (!pos) { if (S->orig) cudaFree(S->orig); S->orig = nullptr; return 0; }
+    if (!S->orig) NGPD_CUDA_OK(cudaMalloc(&S->orig, (size_t)S->n * sizeof(float4)));
+    session_scatter_in_kernel<<<(unsigned)cdiv(S->n, 256), 256, 0, (cudaStream_t)stream_>>>(S->grid->pts, pos, nullptr, S->n, S->orig, nullptr);
+    NGPD_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
@@ -965,12 +1185,11 @@ static int step_tail(ngpd_session_t* S, const ngpd_step_params_t* p, void* strea
     int rc;
     if ((rc = ngpd_session_phase_features(S, p, 1, stream_))) return rc;
     for (int key = 0; key < 3; ++key) {
-        if (p->strategy[key] < 0) continue;
         if (p->strategy[key] == NGPD_STEP_FLAT) {
             if ((rc = ngpd_session_phase_flat_scalars(S, p, key, 0, stream_))) return rc;
             if ((rc = ngpd_session_phase_flat_scalars(S, p, key, 1, stream_))) return rc;
         }
-        if ((rc = ngpd_session_phase_update(S, p, key, stream_))) return rc;
+        if ((rc = ngpd_session_phase_update(S, p, key, stream_))) return rc;   // (a class without a strategy is left alone in there)
     }
     return ngpd_session_phase_commit_normals(S);
 }
@@ -1092,6 +1311,129 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_import_rows(n
     if (which == 0) S->sums_ready = false;
     session_import_kernel<<<(unsigned)cdiv(m, 256), 256, 0, (cudaStream_t)stream_>>>(dst, rows, m, (const float4*)in4);
     NGPD_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+
+// ---- Morton slabs: wiring, halo refresh, cross-rank scalars and the whole step driven from here -------------------------
+extern "C" __attribute__((visibility("default"))) int64_t ngpd_slab_symm_bytes(int world, int64_t cap) {
+    if (world < 1 || world > SLAB_MAX_WORLD || cap < 0) return -1;
+    return 2 * cap * 16 + 2 * (int64_t)world * 32 + (int64_t)world * 8;
+}
+
+extern "C" __attribute__((visibility("default"))) int ngpd_session_set_slab(ngpd_session_t* S, const ngpd_slab_wiring_t* w, void* stream_) {
+    NGPD_REQUIRE(S, "ngpd_session_set_slab: NULL session");
+    if (!w) { delete S->slab; S->slab = nullptr; return 0; }
+    NGPD_REQUIRE(w->world >= 1 && w->world <= SLAB_MAX_WORLD && w->rank >= 0 && w->rank < w->world, "ngpd_session_set_slab: bad world / rank");
+    NGPD_REQUIRE(w->send_seg_host && w->first_row_host && w->symm_base_host, "ngpd_session_set_slab: NULL table");
+    NGPD_REQUIRE((w->n_send == 0 || w->send_rows) && (w->n_recv == 0 || w->recv_rows) && w->n_recv <= w->cap, "ngpd_session_set_slab: bad row lists");
+    if (!S->slab) S->slab = new SlabDev();
+    SlabDev& d = *S->slab;
+    d.world = w->world; d.rank = w->rank; d.cap = w->cap;
+    for (int q = 0; q <= w->world; ++q) d.seg[q] = w->send_seg_host[q];
+    for (int q = 0; q < w->world; ++q) { d.first_row[q] = w->first_row_host[q]; d.base[q] = w->symm_base_host[q]; }
+    NGPD_REQUIRE(d.seg[w->world] == w->n_send, "ngpd_session_set_slab: send_seg does not add up to n_send");
+    S->slab_send_rows = w->send_rows; S->slab_recv_rows = w->recv_rows;
+    S->slab_n_send = w->n_send; S->slab_n_recv = w->n_recv;
+    S->slab_epoch = 0;
+    if (!S->slab_done) {
+        NGPD_CUDA_OK(cudaMalloc(&S->slab_done, sizeof(unsigned)));
+        NGPD_CUDA_OK(cudaMemsetAsync(S->slab_done, 0, sizeof(unsigned), (cudaStream_t)stream_));
+    }
+    return 0;
+}
+
+static float4* slab_buffer(ngpd_session_t* S, int which) { return which == 0 ? S->pos[S->cur] : (which == 1 ? S->nrm : S->fn); }
+
+// one halo refresh of buffer `which` (0 positions, 1 normals, 2 smoothed normals): every rank must call it in the same order
+extern "C" __attribute__((visibility("default"))) int ngpd_session_slab_refresh(ngpd_session_t* S, int which, void* stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    NGPD_REQUIRE(S && S->slab && which >= 0 && which <= 2, "ngpd_session_slab_refresh: no slab wiring / bad buffer");
+    const SlabDev& d = *S->slab;
+    if (d.world == 1) return 0;
+    ProfScope ps(S, st, 5);
+    const unsigned long long epoch = ++S->slab_epoch;
+    const int parity = (int)(epoch & 1);
+    float4* buf = slab_buffer(S, which);
+    // (grids small enough to be resident at once: the pull kernel's blocks wait for the peers)
+    const int pb = stride_blocks(std::max<int64_t>(S->slab_n_send, 1), 256, 4), qb = stride_blocks(std::max<int64_t>(S->slab_n_recv, 1), 256, 4);
+    slab_push_kernel<<<pb, 256, 0, st>>>(d, buf, S->slab_send_rows, S->slab_n_send, parity, epoch, S->slab_done);
+    slab_pull_kernel<<<qb, 256, 0, st>>>(d, buf, S->slab_recv_rows, S->slab_n_recv, parity, epoch);
+    NGPD_CUDA_OK(cudaGetLastError());
+    if (which == 0) S->sums_ready = false;
+    S->launches += 2;
+    return 0;
+}
+
+// mode 0: buffer 3 (flat-step sums, 4 doubles) <- sum over the ranks; mode 1: buffer 4 [3] (delta) <- max over the ranks
+extern "C" __attribute__((visibility("default"))) int ngpd_session_slab_allreduce(ngpd_session_t* S, int mode, void* stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    NGPD_REQUIRE(S && S->slab && (mode == 0 || mode == 1), "ngpd_session_slab_allreduce: no slab wiring / bad mode");
+    const SlabDev& d = *S->slab;
+    if (d.world == 1) return 0;
+    ProfScope ps(S, st, 5);
+    const unsigned long long epoch = ++S->slab_epoch;
+    slab_allreduce_kernel<<<1, 32, 0, st>>>(d, S->acc, S->cd, mode, (int)(epoch & 1), epoch);
+    NGPD_CUDA_OK(cudaGetLastError());
+    S->launches += 1;
+    return 0;
+}
+
+// ngpd_session_step on one Morton slab: the same phases with the halo refreshes and the cross-rank scalars in between
+// (smoothed normals after the first tensor pass, positions after every class that moved, Processor.py:127-138)
+extern "C" __attribute__((visibility("default"))) int ngpd_session_step_slab(ngpd_session_t* S, const ngpd_step_params_t* p, void* stream_) {
+    NGPD_REQUIRE(S && p && S->slab, "ngpd_session_step_slab: NULL argument / no slab wiring");
+    S->launches = 0;
+    int rc;
+    if ((rc = ngpd_session_phase_features(S, p, 0, stream_))) return rc;
+    if ((rc = ngpd_session_slab_refresh(S, 2, stream_))) return rc;
+    if ((rc = ngpd_session_phase_features(S, p, 1, stream_))) return rc;
+    const bool snapshot = (p->flags & NGPD_STEP_SNAPSHOT_CLASSES) != 0;
+    for (int key = 0; key < 3; ++key) {
+        if (p->strategy[key] == NGPD_STEP_FLAT) {
+            if ((rc = ngpd_session_phase_flat_scalars(S, p, key, 0, stream_))) return rc;
+            if ((rc = ngpd_session_slab_allreduce(S, 0, stream_))) return rc;
+            if ((rc = ngpd_session_phase_flat_scalars(S, p, key, 1, stream_))) return rc;
+            if ((rc = ngpd_session_slab_allreduce(S, 1, stream_))) return rc;
+        }
+        if ((rc = ngpd_session_phase_update(S, p, key, stream_))) return rc;
+        // the class' new positions, before the next class reads them (snapshot mode: nobody reads them before the step ends)
+        const bool moved = p->strategy[key] >= 0;
+        if ((moved && !snapshot) || (snapshot && key == 2))
+            if ((rc = ngpd_session_slab_refresh(S, 0, stream_))) return rc;
+    }
+    return ngpd_session_phase_commit_normals(S);
+}
+
+// max over the owned rows, since the session was created (or this was last reset), of: distance of the k-th neighbour found
+// + distance of the query from its own tree position.  A slab's searches equal the whole cloud's iff this stays below the halo width.
+extern "C" __attribute__((visibility("default"))) int ngpd_session_halo_need(ngpd_session_t* S, int reset, float* out_host, void* stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    NGPD_REQUIRE(S && out_host, "ngpd_session_halo_need: NULL argument");
+    *out_host = 0.0f;
+    if (S->halo_need) {
+        NGPD_CUDA_OK(cudaMemcpyAsync(out_host, S->halo_need, sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (reset) NGPD_CUDA_OK(cudaMemsetAsync(S->halo_need, 0, sizeof(float), st));
+        NGPD_CUDA_OK(cudaStreamSynchronize(st));
+    }
+    return 0;
+}
+
+// global_ids (nullable, device, int64): original index of the session -> id in the whole cloud (slabs); synchronises
+extern "C" __attribute__((visibility("default"))) int ngpd_session_checksum(ngpd_session_t* S, const int64_t* global_ids, uint64_t* out11_host, void* stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    NGPD_REQUIRE(S && out11_host, "ngpd_session_checksum: NULL argument");
+    unsigned long long* d = nullptr;
+    NGPD_CUDA_OK(cudaMallocAsync(&d, CHECKSUM_WORDS * sizeof(unsigned long long), st));
+    cudaError_t e = cudaMemsetAsync(d, 0, CHECKSUM_WORDS * sizeof(unsigned long long), st);
+    if (e == cudaSuccess) {
+        session_checksum_kernel<<<strided(S->n, 256), 256, 0, st>>>(S->grid->pts, S->pos[S->cur], S->nrm, S->label, S->owned, global_ids, S->n, d);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out11_host, d, CHECKSUM_WORDS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFreeAsync(d, st);
+    NGPD_CUDA_OK(e);
     return 0;
 }
 

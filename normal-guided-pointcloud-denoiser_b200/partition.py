@@ -95,6 +95,128 @@ class SlabPlan:
         return out
 
 
+
+# ------------------------------------------------------------------------------------------------------
+# planning from SHARDED input: no rank ever holds more than its slab + halo (+ the shard it was handed)
+# ------------------------------------------------------------------------------------------------------
+def _route(tensors, dest: torch.Tensor, world: int, group):
+    """Send row i of every tensor to rank dest[i] (one variable-split all-to-all per tensor).  Returns (received tensors,
+    rows received from each rank); rows arrive grouped by source rank, in the source's order."""
+    order = torch.argsort(dest, stable=True)
+    send_counts = torch.bincount(dest, minlength=world)
+    recv_counts = torch.empty_like(send_counts)
+    dist.all_to_all_single(recv_counts, send_counts, group=group)
+    sc, rc = [int(v) for v in send_counts.tolist()], [int(v) for v in recv_counts.tolist()]
+    out = []
+    for t in tensors:
+        src = t[order].contiguous()
+        dst = torch.empty((sum(rc),) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_to_all_single(dst, src, output_split_sizes=rc, input_split_sizes=sc, group=group)
+        out.append(dst)
+    return out, rc
+
+
+def _all_gather_var(t: torch.Tensor, world: int, group):
+    """all-gather of 1-D tensors of different lengths -> list of tensors"""
+    size = torch.tensor([t.numel()], dtype=torch.long, device=t.device)
+    sizes = [torch.empty_like(size) for _ in range(world)]
+    dist.all_gather(sizes, size, group=group)
+    sizes = [int(v.item()) for v in sizes]
+    pad = torch.zeros(max(max(sizes), 1), dtype=t.dtype, device=t.device)
+    pad[:t.numel()] = t
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad, group=group)
+    return [b[:m] for b, m in zip(bufs, sizes)]
+
+
+def sample_splitters(keys: torch.Tensor, world: int, group, samples: int = 1 << 16) -> torch.Tensor:
+    """world - 1 Morton keys that cut the union of every rank's `keys` into world slabs of nearly equal size: every rank
+    contributes `samples` evenly spaced quantiles of its own keys, weighted by the rows each stands for, and the cuts are
+    read off the merged sample.  Imbalance <= world^2 / samples of a slab."""
+    m = keys.numel()
+    srt = torch.sort(keys).values
+    take = min(samples, m)
+    if take > 0:
+        pick = ((torch.arange(take, device=keys.device, dtype=torch.float64) + 0.5) * (m / take)).long().clamp_(0, m - 1)
+        smp, wgt = srt[pick], torch.full((take,), m / take, dtype=torch.float64, device=keys.device)
+    else:
+        smp, wgt = srt[:0], torch.zeros(0, dtype=torch.float64, device=keys.device)
+    all_s = torch.cat(_all_gather_var(smp, world, group))
+    all_w = torch.cat(_all_gather_var(wgt, world, group))
+    o = torch.argsort(all_s, stable=True)
+    all_s, cum = all_s[o], torch.cumsum(all_w[o], 0)
+    total = float(cum[-1]) if cum.numel() else 0.0
+    targets = torch.tensor([total * r / world for r in range(1, world)], dtype=torch.float64, device=keys.device)
+    at = torch.searchsorted(cum, targets).clamp_(max=max(all_s.numel() - 1, 0))
+    return all_s[at] if all_s.numel() else torch.zeros(world - 1, dtype=torch.long, device=keys.device)
+
+
+class ShardedSlabPlan:
+    """The plan of SlabPlan, built from input that is already spread over the ranks: every rank passes the construction-time
+    positions of ITS shard (any subset; `gids` are the points' ids in the whole cloud) plus per-point payload tensors.
+    Points are routed to the slab that owns their Morton key, halo copies are pushed by their owners.  Communication:
+    a bounding-box all-reduce, one key sample all-gather, and variable-split all-to-alls; memory per rank: shard + slab + halo.
+    Fields as SlabPlan (`owned`, `halo`, `local_ids` hold global ids) plus the routed data: `tree_local` [n_owned + n_halo, 3]
+    and `payload_local`, and the halo wiring itself (`send_local`, `recv_counts`), so HaloExchanger needs no request round."""
+
+    def __init__(self, tree_pos: torch.Tensor, gids: torch.Tensor, halo_width: float, group=None, payload=()):
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        dev = tree_pos.device
+        self.rank, self.world, self.halo_width = rank, world, float(halo_width)
+        lo = tree_pos.min(dim=0).values if tree_pos.numel() else torch.full((3,), float("inf"), device=dev)
+        hi = tree_pos.max(dim=0).values if tree_pos.numel() else torch.full((3,), float("-inf"), device=dev)
+        cnt = torch.tensor([tree_pos.size(0)], dtype=torch.long, device=dev)
+        if world > 1:
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+            dist.all_reduce(cnt, group=group)
+        self.n = int(cnt.item())
+        self.lo, self.hi = lo, hi
+        keys = morton_keys(tree_pos, lo, hi)
+        data = [gids.long(), tree_pos] + list(payload)
+        if world > 1:
+            self.splitters = sample_splitters(keys, world, group)
+            dest = torch.bucketize(keys, self.splitters, right=True)
+            del keys
+            data, _ = _route(data, dest, world, group)
+            del dest
+        o = torch.argsort(data[0])                                  # deterministic local order whatever the sharding was
+        data = [t[o] for t in data]
+        self.owned = data[0]
+        self.n_owned = self.owned.numel()
+        own_tree = data[1]
+        # halo: every owned point whose coarse cell (edge = halo width) lies in the 27-neighbourhood of a cell another rank occupies
+        w = self.halo_width
+        cell = ((own_tree.double() - lo.double()) / w).floor_().long() + 1
+        dims = ((hi.double() - lo.double()) / w).floor_().long() + 3
+        lin = (cell[:, 2] * dims[1] + cell[:, 1]) * dims[0] + cell[:, 0]
+        self.send_local = [torch.empty(0, dtype=torch.long, device=dev) for _ in range(world)]
+        halo_data = [t[:0] for t in data]
+        self.recv_counts = [0] * world
+        if world > 1:
+            mine = torch.unique(lin)
+            offs = torch.tensor([(dz * int(dims[1]) + dy) * int(dims[0]) + dx for dz in (-1, 0, 1) for dy in (-1, 0, 1) for dx in (-1, 0, 1)],
+                                device=dev)
+            near = torch.unique((mine[:, None] + offs[None, :]).reshape(-1))
+            nears = _all_gather_var(near, world, group)
+            rows, dests = [], []
+            for q in range(world):
+                if q == rank:
+                    continue
+                self.send_local[q] = torch.isin(lin, nears[q]).nonzero().flatten()
+                rows.append(self.send_local[q])
+                dests.append(torch.full_like(self.send_local[q], q))
+            rows, dests = torch.cat(rows), torch.cat(dests)
+            halo_data, self.recv_counts = _route([t[rows] for t in data], dests, world, group)
+        self.halo = halo_data[0]
+        self.n_halo = self.halo.numel()
+        self.halo_owner = torch.repeat_interleave(torch.arange(world, device=dev), torch.tensor(self.recv_counts, device=dev))
+        self.local_ids = torch.cat([self.owned, self.halo])
+        self.tree_local = torch.cat([own_tree, halo_data[1]])
+        self.payload_local = [torch.cat([a, b]) for a, b in zip(data[2:], halo_data[2:])]
+
+
 class HaloExchanger:
     """Fixed send/recv wiring between slabs.  `send_local[q]` = local indices (of owned points) whose values go to
     peer q; `recv_local[q]` = local indices (of halo points) that peer q fills, in matching order."""
@@ -102,6 +224,16 @@ class HaloExchanger:
     def __init__(self, plan: SlabPlan, group=None):
         self.plan, self.group = plan, group
         world, rank, dev = plan.world, plan.rank, plan.local_ids.device
+        if hasattr(plan, "send_local"):
+            # ShardedSlabPlan: the owners chose the halo rows themselves, nothing to ask for
+            self.send_local = plan.send_local
+            self.send_counts = [int(r.numel()) for r in plan.send_local]
+            self.recv_counts = list(plan.recv_counts)
+            self.recv_local, off = [], plan.n_owned
+            for q in range(world):
+                self.recv_local.append(torch.arange(off, off + self.recv_counts[q], device=dev))
+                off += self.recv_counts[q]
+            return
         counts = torch.tensor([r.numel() for r in plan.request], dtype=torch.long, device=dev)
         all_counts = [torch.empty_like(counts) for _ in range(world)]
         if world > 1:
@@ -137,29 +269,17 @@ class HaloExchanger:
         dist.all_to_all_single(recv_buf, send_buf, output_split_sizes=self.recv_counts, input_split_sizes=self.send_counts,
                                group=self.group)
 
-    # -- halo push over peer memory (opt-in: SlabSession(transport="peer")) ---------------------------------------------
-    def enable_peer_push(self, device: torch.device):
-        """Symmetric receive buffers (two, used alternately) that the peers' export kernels write into directly
-        (`ngpd_session_export_rows_peers`): one kernel + one cross-rank barrier per exchange instead of gather kernel ->
-        NCCL all-to-all -> scatter.  Double buffering: a peer may already be pushing exchange t+1 while this rank still
-        unpacks exchange t (the barrier only orders a rank's unpacking after everybody's pushing)."""
-        import torch.distributed._symmetric_memory as symm
+    # -- halo push over peer memory (SlabSession(transport="peer"), the default on GPUs) ---------------------------------------
+    def peer_layout(self, device: torch.device):
+        """(cap, first_row, seg) of the peer-memory push, from one all-gather of the receive counts (peer_push_layout)."""
         world, rank = self.plan.world, self.plan.rank
-        group = self.group if self.group is not None else dist.group.WORLD
         mine = torch.tensor(self.recv_counts, dtype=torch.long, device=device)
         table = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(table, mine, group=group)
+        dist.all_gather(table, mine, group=self.group)
         recv = [[int(v) for v in t.tolist()] for t in table]              # recv[q][s] = rows rank q receives from rank s
         cap, first_row, seg = peer_push_layout(recv, rank)
         assert seg[1:] == [sum(self.send_counts[:q + 1]) for q in range(world)]
-        self._sym = symm.empty((2, cap, 4), dtype=torch.float32, device=device)
-        self._hdl = symm.rendezvous(self._sym, group)
-        ptrs = [int(a) for a in self._hdl.buffer_ptrs]
-        self._peer_base = [torch.tensor([ptrs[q] + 16 * (b * cap + first_row[q]) for q in range(world)],
-                                        dtype=torch.int64, device=device) for b in range(2)]
-        self._seg = torch.tensor(seg, dtype=torch.long, device=device)
-        self._parity = 0
-        self.peer = True
+        return cap, first_row, seg
 
     def bytes_per_exchange(self, row_bytes: int = 16):
         return sum(self.send_counts) * row_bytes, sum(self.recv_counts) * row_bytes
@@ -183,12 +303,27 @@ def estimate_halo_width(tree_pos: torch.Tensor, k: int, factor: float = 6.0) -> 
     """A safe halo width: `factor` times the typical k-NN radius, estimated from the bounding-box surface density
     (the same first guess the grid builder uses).  The k-NN radius of a moved query must stay below
     halo_width - displacement for the slab result to equal the single-GPU one; SlabSession checks that."""
-    ext = (tree_pos.max(dim=0).values - tree_pos.min(dim=0).values).double()
+    return halo_width_from_box(tree_pos.min(dim=0).values, tree_pos.max(dim=0).values, tree_pos.size(0), k, factor)
+
+
+def halo_width_from_box(lo: torch.Tensor, hi: torch.Tensor, n: int, k: int, factor: float = 6.0) -> float:
+    ext = (hi - lo).double()
     area = float(2 * (ext[0] * ext[1] + ext[1] * ext[2] + ext[2] * ext[0]))
     if area <= 0:
         area = float(ext.max()) ** 2
-    spacing = math.sqrt(area / tree_pos.size(0))
+    spacing = math.sqrt(area / max(n, 1))
     return factor * spacing * math.sqrt(k / math.pi)
+
+
+def estimate_halo_width_sharded(tree_pos: torch.Tensor, k: int, group=None, factor: float = 6.0) -> float:
+    """estimate_halo_width when every rank holds only a shard of the cloud"""
+    lo, hi = tree_pos.min(dim=0).values, tree_pos.max(dim=0).values
+    cnt = torch.tensor([tree_pos.size(0)], dtype=torch.long, device=tree_pos.device)
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+        dist.all_reduce(cnt, group=group)
+    return halo_width_from_box(lo, hi, int(cnt.item()), k, factor)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -238,21 +373,37 @@ class _DevView:
 class SlabSession:
     """One rank's share of a denoising run: owned slab + halo in one CUDA session, halos refreshed between phases."""
 
-    def __init__(self, pos: torch.Tensor, nrm: torch.Tensor, k_feature=16, k_update=8, alphas=(1.0, 0.2, 1.0),
+    def __init__(self, pos: torch.Tensor, nrm: torch.Tensor | None, k_feature=16, k_update=8, alphas=(1.0, 0.2, 1.0),
                  strategy=None, halo_width: float | None = None, group=None, tree_pos: torch.Tensor | None = None,
-                 transport: str | None = None):
+                 transport: str | None = None, shard_ids: torch.Tensor | None = None, mean_edge_length: float | None = None,
+                 flags: int = 0, clamp_radius: float = 0.0):
+        """Replicated input (shard_ids None): every rank passes the WHOLE cloud and keeps its slab (small clouds, tests).
+        Sharded input: every rank passes any part of the cloud with the points' global ids in `shard_ids`; rows are routed
+        to their slabs (ShardedSlabPlan) and no rank holds more than shard + slab + halo.  nrm None: normals are set later
+        (set_owned_normals / pca_normals)."""
         from . import _lib
         self._lib = _lib
         self.group = group
         world = dist.get_world_size(group) if dist.is_initialized() else 1
         rank = dist.get_rank(group) if dist.is_initialized() else 0
         tree = pos if tree_pos is None else tree_pos
-        hw = halo_width if halo_width is not None else estimate_halo_width(tree, k_feature)
-        self.plan = SlabPlan(tree, rank, world, hw)
+        if shard_ids is None:
+            hw = halo_width if halo_width is not None else estimate_halo_width(tree, k_feature)
+            self.plan = SlabPlan(tree, rank, world, hw)
+            ids = self.plan.local_ids
+            tree_l, pos_l, nrm_l = tree[ids].contiguous(), pos[ids].contiguous(), (nrm[ids].contiguous() if nrm is not None else None)
+        else:
+            hw = halo_width if halo_width is not None else estimate_halo_width_sharded(tree, k_feature, group)
+            payload = ([pos] if tree_pos is not None else []) + ([nrm] if nrm is not None else [])
+            self.plan = ShardedSlabPlan(tree, shard_ids, hw, group, payload)
+            tree_l = self.plan.tree_local.contiguous()
+            rest = list(self.plan.payload_local)
+            pos_l = rest.pop(0).contiguous() if tree_pos is not None else tree_l
+            nrm_l = rest.pop(0).contiguous() if nrm is not None else None
         self.n_owned, self.n_halo, self.n_total = self.plan.n_owned, self.plan.n_halo, self.plan.n
-        ids = self.plan.local_ids
-        self.session = _lib.Session(tree[ids].contiguous(), k_feature)
-        self.session.set_state(pos[ids].contiguous(), nrm[ids].contiguous())
+        self.tree_local = tree_l
+        self.session = _lib.Session(tree_l, k_feature)
+        self.session.set_state(pos_l, nrm_l)
         self.ex = HaloExchanger(self.plan, group)
         dev = pos.device
         # local index -> session tree position
@@ -268,24 +419,88 @@ class SlabSession:
         self._recv_rows = torch.cat([inv[r] for r in self.ex.recv_local]).to(torch.int32).contiguous()
         self._send_buf = torch.empty((self._send_rows.numel(), 4), dtype=torch.float32, device=dev)
         self._recv_buf = torch.empty((self._recv_rows.numel(), 4), dtype=torch.float32, device=dev)
-        # halo transport: "nccl" = gather kernel + one all-to-all + scatter kernel; "peer" = the gather kernel stores into the
-        # peers' receive buffers itself (symmetric memory over NVLink) and a cross-rank barrier replaces the collective
-        transport = transport or os.environ.get("NGPD_HALO_TRANSPORT", "nccl")
+        # halo transport.  "peer" (default): the whole step is driven from C (ngpd_session_step_slab); halo rows are stored
+        # straight into the peers' receive buffers (symmetric memory over NVLink / NVSwitch), signalled with release stores and
+        # awaited with acquire loads, and flat_step's two cloud-wide scalars go through the same block -- no NCCL call, no host
+        # round trip inside an iteration.  "nccl": gather kernel + one all-to-all + scatter kernel per refresh and two
+        # all-reduces, phase by phase from Python (the round-1 path; also what the gloo tests exercise on the CPU side).
+        transport = transport or os.environ.get("NGPD_HALO_TRANSPORT", "peer")
         assert transport in ("nccl", "peer"), transport
         self.transport = transport if world > 1 else "nccl"
         if self.transport == "peer":
-            self.ex.enable_peer_push(dev)
+            self._wire_peer(dev)
         self._inv = inv
-        # global d = 2 * mean 6-NN edge length (Processor.py:120-121)
-        s, c = self.session.mean_edge_length_parts(6)
-        t = torch.tensor([s, c], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, group=group)
-        self.mean_edge_length = float(t[0] / t[1])
-        st = strategy if strategy is not None else (_lib.STEP_FLAT, _lib.STEP_EDGE, _lib.STEP_FEATURE)
-        self.params = _lib.make_params(k_feature, k_update, None, 0.3, 3.0, 0.2, st, alphas, 2.0 * self.mean_edge_length)
         self.world, self.rank = world, rank
         self.exchanges = 0
+        # global d = 2 * mean 6-NN edge length (Processor.py:120-121)
+        if mean_edge_length is None:
+            s, c = self.session.mean_edge_length_parts(6)
+            t = torch.tensor([s, c], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, group=group)
+            mean_edge_length = float(t[0] / t[1])
+        self.mean_edge_length = mean_edge_length
+        st = strategy if strategy is not None else (_lib.STEP_FLAT, _lib.STEP_EDGE, _lib.STEP_FEATURE)
+        self.params = _lib.make_params(k_feature, k_update, None, 0.3, 3.0, 0.2, st, alphas, 2.0 * self.mean_edge_length, flags, clamp_radius)
+
+    def set_owned_normals(self, nrm_owned: torch.Tensor):
+        """normals of the owned rows (slab order = plan.owned); the halo copies are fetched from their owners"""
+        full = torch.zeros((self.n_owned + self.n_halo, 3), dtype=torch.float32, device=nrm_owned.device)
+        full[:self.n_owned] = nrm_owned
+        self.session.set_state(None, full)
+        self._refresh(1)
+
+    def pca_normals(self, k: int = 12, orient_like: torch.Tensor | None = None) -> torch.Tensor:
+        """GraphBuilder.getKNNEdgeIndex(k) + setPVTNormals on the slab (GraphBuilder.py:60-63, 95-111): k-NN graph without
+        self over the construction-time positions, PCA normal per owned row, optionally flipped to agree with `orient_like`
+        (owned rows); sets them as the session's normals and returns them."""
+        L = self._lib
+        tree = self.tree_local
+        grid = L.Grid(tree, k)
+        table = grid.knn(tree[:self.n_owned].contiguous(), k, L.KNN_SKIP_SELF)
+        nrm = torch.empty((self.n_owned, 3), dtype=torch.float32, device=tree.device)
+        with torch.cuda.device(tree.device):
+            L.check(L.load().ngpd_pca_normals(tree.data_ptr(), table.data_ptr(), None, self.n_owned, k, nrm.data_ptr(), None, None, L.stream()),
+                    "ngpd_pca_normals")
+        if orient_like is not None:
+            flip = (nrm * orient_like).sum(1) < 0
+            nrm[flip] *= -1
+        del grid, table
+        self.set_owned_normals(nrm)
+        return nrm
+
+    def checksum(self) -> list[int]:
+        """digest of the whole cloud's state (every rank gets it): per-slab digests add up modulo 2^64"""
+        part = self.session.checksum(self.plan.local_ids)
+        t = torch.tensor([v - (1 << 64) if v >= (1 << 63) else v for v in part], dtype=torch.int64, device=self._send_buf.device)
+        if self.world > 1:
+            dist.all_reduce(t, group=self.group)
+        return [int(v) & ((1 << 64) - 1) for v in t.tolist()]
+
+    def _wire_peer(self, dev):
+        """One block of symmetric memory per rank (receive buffers of the halo rows, scalar slots, round flags: include/ngpd.h,
+        ngpd_slab_wiring_t), mapped into every peer; the addresses go to the session once."""
+        import ctypes
+        import torch.distributed._symmetric_memory as symm
+        L, lib = self._lib, self._lib.load()
+        world, rank = self.plan.world, self.plan.rank
+        group = self.group if self.group is not None else dist.group.WORLD
+        cap, first_row, seg = self.ex.peer_layout(dev)
+        nbytes = int(lib.ngpd_slab_symm_bytes(world, cap))
+        assert nbytes > 0
+        self._sym = symm.empty(((nbytes + 15) // 16 * 16,), dtype=torch.uint8, device=dev)
+        self._sym.zero_()
+        self._hdl = symm.rendezvous(self._sym, group)
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=group)                              # everybody's flags are zero before anybody signals
+        ptrs = [int(a) for a in self._hdl.buffer_ptrs]
+        w = L.SlabWiring()
+        w.world, w.rank, w.n_send, w.n_recv, w.cap = world, rank, self._send_rows.numel(), self._recv_rows.numel(), cap
+        w.send_rows, w.recv_rows = self._send_rows.data_ptr(), self._recv_rows.data_ptr()
+        self._wire_keep = ((ctypes.c_int64 * (world + 1))(*seg), (ctypes.c_int64 * world)(*first_row), (ctypes.c_uint64 * world)(*ptrs))
+        w.send_seg_host, w.first_row_host, w.symm_base_host = self._wire_keep
+        with torch.cuda.device(dev):
+            L.check(lib.ngpd_session_set_slab(self.session._h, ctypes.byref(w), L.stream()), "ngpd_session_set_slab")
 
     # -- halo refresh of session buffer `which` (0 positions, 1 normals, 2 smoothed normals) -----------------
     def _refresh(self, which: int):
@@ -294,14 +509,7 @@ class SlabSession:
         lib, L = self._lib.load(), self._lib
         h = self.session._h
         if self.transport == "peer":
-            ex = self.ex
-            b = ex._parity
-            ex._parity ^= 1
-            L.check(lib.ngpd_session_export_rows_peers(h, which, self._send_rows.data_ptr(), self._send_rows.numel(), ex._seg.data_ptr(),
-                                                       ex._peer_base[b].data_ptr(), self.world, L.stream()), "ngpd_session_export_rows_peers")
-            ex._hdl.barrier(channel=0)                          # every rank's stores have landed before anybody unpacks
-            L.check(lib.ngpd_session_import_rows(h, which, self._recv_rows.data_ptr(), self._recv_rows.numel(), ex._sym[b].data_ptr(), L.stream()),
-                    "ngpd_session_import_rows")
+            L.check(lib.ngpd_session_slab_refresh(h, which, L.stream()), "ngpd_session_slab_refresh")
             self.exchanges += 1
             return
         L.check(lib.ngpd_session_export_rows(h, which, self._send_rows.data_ptr(), self._send_rows.numel(), self._send_buf.data_ptr(), L.stream()),
@@ -327,6 +535,9 @@ class SlabSession:
         h, st = self.session._h, L.stream
         self.launches = 0
         ref = ctypes.byref(p)
+        if self.transport == "peer":
+            L.check(lib.ngpd_session_step_slab(h, ref, st()), "ngpd_session_step_slab")
+            return
         L.check(lib.ngpd_session_phase_features(h, ref, 0, st()), "phase_features 0")
         self._refresh(2)                                        # neighbours' smoothed normals
         L.check(lib.ngpd_session_phase_features(h, ref, 1, st()), "phase_features 1")
@@ -344,6 +555,19 @@ class SlabSession:
             L.check(lib.ngpd_session_phase_update(h, ref, key, st()), "phase_update")
             self._refresh(0)                                    # the class' new positions, before the next class reads them
         L.check(lib.ngpd_session_phase_commit_normals(h), "commit normals")
+
+    def verify_halo(self) -> float:
+        """The slab searches equal the whole cloud's iff every owned row's (k-th neighbour distance + displacement from its
+        tree position) stayed below the halo width (the session tracks the maximum, ngpd_session_halo_need).  Returns the
+        largest value any rank has seen; raises on every rank when it reached the width."""
+        need = torch.tensor([self.session.halo_need()], dtype=torch.float64, device=self._send_buf.device)
+        if self.world > 1:
+            dist.all_reduce(need, op=dist.ReduceOp.MAX, group=self.group)
+        need = float(need.item())
+        if not need < self.plan.halo_width:
+            raise RuntimeError(f"halo too narrow: a query needed points up to {need:.6g} from its tree position, the halo is "
+                               f"{self.plan.halo_width:.6g} wide -- rebuild the SlabSession with halo_width > {need:.6g}")
+        return need
 
     def owned_state(self):
         """(original ids, positions, normals, labels) of the owned points"""
