@@ -66,6 +66,12 @@ int ngpd_knn(const ngpd_grid_t* grid, const float* query, int64_t m, int k, int 
 int ngpd_nn_sqdist(const ngpd_grid_t* grid, const float* query, int64_t m, int flags,
                    float* d2_out, int32_t* idx_out, void* stream);
 
+/* ngpd_nn_sqdist with the reduction the metrics' callers apply fused in (Utils.py:253-295: .mean() for Chamfer / sCD, .max() for
+ * Hausdorff): acc4_out (device, 4 doubles) = {sum d2, sum d, max d2, rows}, summed in a fixed order.  d2_out, idx_out nullable:
+ * a Chamfer evaluation at 10^9 points needs no per-point output at all. */
+int ngpd_nn_sqdist_reduce(const ngpd_grid_t* grid, const float* query, int64_t m, int flags,
+                          float* d2_out, int32_t* idx_out, double* acc4_out, void* stream);
+
 /* radius selection: replaces scipy KDTree.query_ball_point(pos, radii) behind Selector.getPointsInRangeSelectionVectorized,
  * Selector.py:214-229 (the Yadav-2018 baseline path).  Row q = every tree point with fp64 squared
  * distance <= radii[q]^2, ascending by index (SciPy's order for multi-point queries).  Two passes:
@@ -170,6 +176,8 @@ typedef struct ngpd_step_params {
 
 int ngpd_session_create(const float* tree_pos, int64_t n, int k_hint, void* stream, ngpd_session_t** out);
 int ngpd_session_destroy(ngpd_session_t* s);
+/* allocate now what a step with this neighbourhood size would allocate on first use (optional) */
+int ngpd_session_reserve(ngpd_session_t* s, int k_feature, void* stream);
 int ngpd_session_set_state(ngpd_session_t* s, const float* pos, const float* nrm, void* stream);
 int ngpd_session_get_state(ngpd_session_t* s, float* pos_out, float* nrm_out, uint8_t* labels_out, void* stream);
 /* one iteration: kNN(k_feature) -> NVT -> smooth -> NVT -> classify -> class-sequential update; normals <- smoothed */
@@ -202,7 +210,7 @@ int ngpd_session_order(const ngpd_session_t* s, int32_t* perm_out, void* stream)
  *   phase_features part 0: kNN(k_feature) + NVT on the current normals + smoothing  -> smoothed normals
  *                  part 1: NVT on the smoothed normals -> labels + crease directions
  *   phase_flat_scalars (only for a class whose strategy is NGPD_STEP_FLAT, Denoiser.py:106-107)
- *                  part 0: {sum x, sum y, sum z, count} of the class' gathered neighbours -> buffer 3 (4 doubles)
+ *                  part 0: {sum x, sum y, sum z, count} of the class' gathered neighbours -> buffer 3 (4 x int64, fixed point)
  *                  part 1: centre = sums/count, then max distance from it -> buffer 4 (4 floats: centre, delta)
  *                  a multi-GPU driver all-reduces buffer 3 (sum) between the parts and buffer 4[3] (max) after
  *   phase_update: class `key` moves, everything else is copied into the other position buffer
@@ -215,7 +223,8 @@ int ngpd_session_phase_commit_normals(ngpd_session_t* s);
  * (read-only for this rank).  NULL clears the mask. */
 int ngpd_session_set_owned(ngpd_session_t* s, const uint8_t* owned_tree_order, void* stream);
 /* device views of session state in tree order: 0 positions (float4), 1 normals (float4), 2 smoothed normals
- * (float4), 3 flat-step accumulators (4 doubles), 4 centre+delta (4 floats), 5 labels (u8), 6 neighbour table,
+ * (float4), 3 flat-step accumulators (4 x int64: sum x, y, z in fixed point + neighbour count -- exact, so the sum over slabs
+ * equals the whole cloud's bit for bit), 4 centre+delta (4 floats), 5 labels (u8), 6 neighbour table,
  * 7 hand-over lists of the last kNN pass (int32: n rows each of tiers 0, 1, 2, then the three counters; diagnostics) */
 void* ngpd_session_buffer(ngpd_session_t* s, int which);
 /* halo traffic: gather / scatter float4 rows of buffer `which` (0..2) listed by tree position */

@@ -37,6 +37,28 @@ class Processor:
             self._session = _lib.Session(self.selector.tree_pos, k_hint=16)
         return self._session
 
+    def denoiseOurs(self, iterations: int = 2, original_pos: torch.Tensor | None = None, strategy=None, alphas=(1.0, 0.2, 1.0)):
+        """The thesis' final strategy as the notebook runs it (PostProcessing.ipynb#c9, row "Ours"; not a method of the
+        reference's Processor): per iteration flat_step for class 0 and feature_step for classes 1 and 2 with d * 20000, all
+        from one snapshot of the positions, then the displacement clamp |x_new - x_original| < d.  One fused session step per
+        iteration (NGPD_STEP_SNAPSHOT_CLASSES + clamp_radius).  strategy: Denoiser step per class, default flat/feature/feature."""
+        g = self.graph
+        sess = self._get_session()
+        sess.set_state(g.pos, g.n)
+        sess.set_original(g.pos if original_pos is None else original_pos)
+        d = 2.0 * self._mean_edge_length(6)
+        dn = self.denoiser
+        funcs = strategy if strategy is not None else (dn.flat_step, dn.feature_step, dn.feature_step)
+        kinds = [self._kind_of(f) for f in funcs]
+        assert None not in kinds, "denoiseOurs: strategy entries must be Denoiser steps"
+        params = _lib.make_params(16, 8, None, 0.3, 3.0, 0.2, kinds, alphas, d * 20000.0, _lib.STEP_SNAPSHOT_CLASSES, d)
+        for _ in range(iterations):
+            sess.step(params)
+        pos, nrm, _ = sess.get_state(False)
+        sess.set_original(None)
+        g.pos.copy_(pos)
+        g.n = nrm
+
     def _kind_of(self, func) -> int | None:
         d = self.denoiser
         table = {d.flat_step: _lib.STEP_FLAT, d.edge_step: _lib.STEP_EDGE, d.feature_step: _lib.STEP_FEATURE,
@@ -107,7 +129,10 @@ class Processor:
         g = self.graph
         noisy_pos, noisy_n = g.pos.clone(), g.n.clone()
         kinds = [_lib.STEP_NONE] * 3
-        fused = True
+        # the fused session moves the classes in the order 0, 1, 2 from rows that are prefixes of the 16-NN rows: a strategy
+        # dict in another order (the reference walks strategy.items(), and the classes move in place one after the other) or a
+        # wider update neighbourhood goes through the public operators instead
+        fused = list(strategy) == sorted(strategy) and 1 <= k <= 16
         for key, func in strategy.items():
             kind = self._kind_of(func)
             if kind is None or key not in (0, 1, 2):
@@ -156,30 +181,6 @@ class Processor:
                 new_pos = func(selection.filter(indices), f_n, d, alpha[key])
             g.pos[indices] = new_pos
         return f_n
-
-    def denoise_unfused(self, k_feature: int = 16, k_update: int = 8, iterations: int = 2):
-        """Processor.denoise written against the public operators, call for call as the reference does it
-        (:119-139); used to cross-check the fused session."""
-        g = self.graph
-        l = TorchUtils.averageEdgeLength(g.pos, self.selector.getKNNSelection(6).getEdgeIndex())
-        d = float(2 * l)
-        alphas = [1, 0.2, 1]
-        for _ in range(iterations):
-            decomposition, f_n = self.getMyFeatureDecomposition(k_feature)
-            classes = decomposition.getClasses()
-            selection = self.selector.getKNNSelection(k_update)
-            for key in range(3):
-                indices = (classes == key).nonzero().flatten()
-                if indices.size(0) == 0:
-                    continue
-                if key == 0:
-                    new_pos = self.denoiser.flat_step(selection.filter(indices), f_n, d, alphas[key])
-                elif key == 1:
-                    new_pos = self.denoiser.edge_step(selection.filter(indices), f_n, decomposition.eigvec[..., 0], d, alphas[key])
-                else:
-                    new_pos = self.denoiser.feature_step(selection.filter(indices), f_n, d, alphas[key])
-                g.pos[indices] = new_pos
-            g.n = f_n
 
     def preprocessPointcloud(self, k: int = 12, noise_level: float = 0.3):
         """(:187-199) kNN graph + PCA normals on the clean cloud, Gaussian noise along the normal of

@@ -45,6 +45,7 @@ SIGNATURES = {
     "ngpd_grid_order": (ctypes.c_int, [c_vp, c_vp, c_vp]),
     "ngpd_knn": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.c_int, ctypes.c_int, c_vp, c_vp, c_vp]),
     "ngpd_nn_sqdist": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.c_int, c_vp, c_vp, c_vp]),
+    "ngpd_nn_sqdist_reduce": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.c_int, c_vp, c_vp, c_vp, c_vp]),
     "ngpd_ball_query": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, ctypes.c_int, c_vp, c_vp, c_vp, c_vp]),
     "ngpd_nvt_normal": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.c_int, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ngpd_pvt_normal": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.c_int, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
@@ -60,6 +61,7 @@ SIGNATURES = {
     "ngpd_edge_length_sum": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, ctypes.c_int, c_vp, c_vp]),
     "ngpd_session_create": (ctypes.c_int, [c_vp, c_i64, ctypes.c_int, c_vp, ctypes.POINTER(c_vp)]),
     "ngpd_session_destroy": (ctypes.c_int, [c_vp]),
+    "ngpd_session_reserve": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp]),
     "ngpd_session_set_state": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp]),
     "ngpd_session_get_state": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ngpd_session_set_owned": (ctypes.c_int, [c_vp, c_vp, c_vp]),
@@ -185,15 +187,16 @@ class Grid:
         r = dev(radii, torch.float32, "radii")
         m = q.size(0)
         assert r.dim() == 1 and r.size(0) == m
-        counts = torch.empty(m, dtype=torch.int32, device=q.device)
-        check(load().ngpd_ball_query(self._h, ptr(q), m, ptr(r), flags, ptr(counts), None, None, stream()), "ngpd_ball_query")
-        total = int(counts.sum(dtype=torch.int64).item())
-        if total >= 2 ** 31:
-            raise NgpdError(f"ngpd_ball_query: {total} neighbours do not fit the int32 offsets of the neighbourhood kernels")
-        offsets = torch.zeros(m + 1, dtype=torch.int32, device=q.device)
-        offsets[1:] = torch.cumsum(counts, 0, dtype=torch.int64).to(torch.int32)
-        idx = torch.empty(max(total, 1), dtype=torch.int32, device=q.device)
-        check(load().ngpd_ball_query(self._h, ptr(q), m, ptr(r), flags, None, ptr(offsets), ptr(idx), stream()), "ngpd_ball_query")
+        with torch.cuda.device(q.device):
+            counts = torch.empty(m, dtype=torch.int32, device=q.device)
+            check(load().ngpd_ball_query(self._h, ptr(q), m, ptr(r), flags, ptr(counts), None, None, stream()), "ngpd_ball_query")
+            total = int(counts.sum(dtype=torch.int64).item())
+            if total >= 2 ** 31:
+                raise NgpdError(f"ngpd_ball_query: {total} neighbours do not fit the int32 offsets of the neighbourhood kernels")
+            offsets = torch.zeros(m + 1, dtype=torch.int32, device=q.device)
+            offsets[1:] = torch.cumsum(counts, 0, dtype=torch.int64).to(torch.int32)
+            idx = torch.empty(max(total, 1), dtype=torch.int32, device=q.device)
+            check(load().ngpd_ball_query(self._h, ptr(q), m, ptr(r), flags, None, ptr(offsets), ptr(idx), stream()), "ngpd_ball_query")
         return idx[:total], offsets
 
     def nn_sqdist(self, query: torch.Tensor, want_idx: bool = False, flags: int = 0):
@@ -204,6 +207,17 @@ class Grid:
         with torch.cuda.device(query.device):
             check(load().ngpd_nn_sqdist(self._h, ptr(query), m, flags, ptr(d2), ptr(idx), stream()), "ngpd_nn_sqdist")
         return (d2, idx) if want_idx else d2
+
+    def nn_reduce(self, query: torch.Tensor, flags: int = 0, want_d2: bool = False):
+        """{sum d2, sum d, max d2, rows} (fp64 device tensor [4]) of the nearest-neighbour pass, optionally with the per-query
+        squared distances: the fused form of `metric(...).mean()` / `.max()`"""
+        query = dev(query, torch.float32, "query")
+        m = query.size(0)
+        acc = torch.empty(4, dtype=torch.float64, device=query.device)
+        d2 = torch.empty(m, dtype=torch.float32, device=query.device) if want_d2 else None
+        with torch.cuda.device(query.device):
+            check(load().ngpd_nn_sqdist_reduce(self._h, ptr(query), m, flags, ptr(d2), None, ptr(acc), stream()), "ngpd_nn_sqdist_reduce")
+        return (acc, d2) if want_d2 else acc
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -281,6 +295,11 @@ class Session:
             check(load().ngpd_session_create(ptr(tree_pos), self.n, int(k_hint), stream(), ctypes.byref(h)),
                   "ngpd_session_create")
         self._h = h
+
+    def reserve(self, k_feature: int):
+        """allocate the step's working buffers now instead of inside the first iteration"""
+        with torch.cuda.device(self.device):
+            check(load().ngpd_session_reserve(self._h, int(k_feature), stream()), "ngpd_session_reserve")
 
     def set_state(self, pos, nrm):
         pos = dev(pos, torch.float32, "pos") if pos is not None else None

@@ -70,6 +70,20 @@ struct Quad4 {
     }
 };
 
+// stream-ordered scratch that is returned on every exit path (early error returns included)
+template <class T>
+struct StreamBuf {
+    T* p = nullptr;
+    cudaStream_t st;
+    explicit StreamBuf(cudaStream_t s) : st(s) {}
+    StreamBuf(const StreamBuf&) = delete;
+    StreamBuf& operator=(const StreamBuf&) = delete;
+    cudaError_t alloc(size_t count) { return cudaMallocAsync(&p, count * sizeof(T), st); }
+    T* release() { T* q = p; p = nullptr; return q; }
+    ~StreamBuf() { if (p) cudaFreeAsync(p, st); }
+    operator T*() const { return p; }
+};
+
 static inline int num_sms() {
     static int n = 0;
     if (!n) {

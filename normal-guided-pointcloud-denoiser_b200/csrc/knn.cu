@@ -102,21 +102,63 @@ __global__ void __launch_bounds__(128) knn_fix_kernel(GridView g, const float* _
     }
 }
 
+// REDUCE: the block also leaves {sum d2, sum d, max d2, rows} in part[4 * blockIdx.x ..] (fp64; added up in a fixed order afterwards)
+template <bool REDUCE>
 __global__ void __launch_bounds__(128) nn_sqdist_kernel(GridView g, const float* __restrict__ query, const int32_t* __restrict__ qorder,
-                                                        int64_t m, float* __restrict__ d2_out, int32_t* __restrict__ idx_out) {
+                                                        int64_t m, float* __restrict__ d2_out, int32_t* __restrict__ idx_out,
+                                                        double* __restrict__ part) {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= m) return;
-    int64_t qi = qorder ? (int64_t)qorder[t] : t;
-    float fx = __ldg(query + 3 * qi), fy = __ldg(query + 3 * qi + 1), fz = __ldg(query + 3 * qi + 2);
-    TopK<1> top;
-    top.init();
-    knn_search<1>(top, g, (double)fx, (double)fy, (double)fz, -1);
-    int j = top.id[0];
-    float4 p = __ldg(g.pts + (j >= 0 ? j : 0));
-    // fp32 recomputation, as the reference does after its 1-NN lookup (Utils.py:262-263)
-    float dx = p.x - fx, dy = p.y - fy, dz = p.z - fz;
-    if (d2_out) d2_out[qi] = (dx * dx + dy * dy) + dz * dz;
-    if (idx_out) idx_out[qi] = j >= 0 ? __float_as_int(p.w) : g.n;
+    float d2 = 0.0f;
+    const bool active = t < m;
+    if (active) {
+        int64_t qi = qorder ? (int64_t)qorder[t] : t;
+        float fx = __ldg(query + 3 * qi), fy = __ldg(query + 3 * qi + 1), fz = __ldg(query + 3 * qi + 2);
+        TopK<1> top;
+        top.init();
+        knn_search<1>(top, g, (double)fx, (double)fy, (double)fz, -1);
+        int j = top.id[0];
+        float4 p = __ldg(g.pts + (j >= 0 ? j : 0));
+        // fp32 recomputation, as the reference does after its 1-NN lookup (Utils.py:262-263)
+        float dx = p.x - fx, dy = p.y - fy, dz = p.z - fz;
+        d2 = (dx * dx + dy * dy) + dz * dz;
+        if (d2_out) d2_out[qi] = d2;
+        if (idx_out) idx_out[qi] = j >= 0 ? __float_as_int(p.w) : g.n;
+    }
+    if (REDUCE) {
+        double s2 = active ? (double)d2 : 0.0, s1 = active ? (double)sqrtf(d2) : 0.0, mx = s2, cnt = active ? 1.0 : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o)); cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        }
+        __shared__ double red[4][4];
+        const int w = threadIdx.x >> 5;
+        if ((threadIdx.x & 31) == 0) { red[w][0] = s2; red[w][1] = s1; red[w][2] = mx; red[w][3] = cnt; }
+        __syncthreads();
+        if (threadIdx.x < 4) {
+            const int c = threadIdx.x;
+            double v = red[0][c];
+            for (int q = 1; q < 4; ++q) v = c == 2 ? fmax(v, red[q][c]) : v + red[q][c];
+            part[(int64_t)blockIdx.x * 4 + c] = v;
+        }
+    }
+}
+// one block: thread t adds blocks t, t + 256, ... in order, then the 256 partial results are added in thread order
+__global__ void __launch_bounds__(256) nn_reduce_kernel(const double* __restrict__ part, int64_t blocks, double* __restrict__ acc4) {
+    __shared__ double sh[256][4];
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int64_t b = threadIdx.x; b < blocks; b += 256) {
+        v[0] += part[b * 4]; v[1] += part[b * 4 + 1]; v[2] = fmax(v[2], part[b * 4 + 2]); v[3] += part[b * 4 + 3];
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) sh[threadIdx.x][c] = v[c];
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        const int c = threadIdx.x;
+        double t = sh[0][c];
+        for (int q = 1; q < 256; ++q) t = c == 2 ? fmax(t, sh[q][c]) : t + sh[q][c];
+        acc4[c] = t;
+    }
 }
 
 __global__ void __launch_bounds__(256) order_from_vals_kernel(const uint32_t* __restrict__ vals, int64_t m, int32_t* __restrict__ out) {
@@ -130,27 +172,25 @@ __global__ void __launch_bounds__(256) order_from_pts_kernel(const float4* __res
 
 // visiting order of the queries: tree order when query i is tree point i, otherwise sorted by the
 // queries' own cell keys; nullptr (identity) for small or already coherent batches
-static int make_query_order(const ngpd_grid* G, const float* query, int64_t m, int flags, cudaStream_t stream, int32_t** order) {
-    *order = nullptr;
-    if ((flags & NGPD_KNN_COHERENT) || m < 2048) return 0;
-    NGPD_CUDA_OK(cudaMallocAsync(order, m * sizeof(int32_t), stream));
+static int make_query_order(const ngpd_grid* G, const float* query, int64_t m, int flags, cudaStream_t stream, StreamBuf<int32_t>& order) {
+    if ((flags & NGPD_KNN_COHERENT) || m < 2048) return 0;       // order stays null = identity
+    NGPD_CUDA_OK(order.alloc(m));
     if ((flags & NGPD_KNN_QUERY_IS_TREE) && m == G->n) {
-        order_from_pts_kernel<<<(unsigned)cdiv(m, 256), 256, 0, stream>>>(G->pts, m, *order);
+        order_from_pts_kernel<<<(unsigned)cdiv(m, 256), 256, 0, stream>>>(G->pts, m, order);
         NGPD_CUDA_OK(cudaGetLastError());
         return 0;
     }
-    uint64_t *keys = nullptr, *keys2 = nullptr;
-    uint32_t *vals = nullptr, *vals2 = nullptr;
-    NGPD_CUDA_OK(cudaMallocAsync(&keys, m * 8, stream)); NGPD_CUDA_OK(cudaMallocAsync(&keys2, m * 8, stream));
-    NGPD_CUDA_OK(cudaMallocAsync(&vals, m * 4, stream)); NGPD_CUDA_OK(cudaMallocAsync(&vals2, m * 4, stream));
+    StreamBuf<uint64_t> keys(stream), keys2(stream);
+    StreamBuf<uint32_t> vals(stream), vals2(stream);
+    NGPD_CUDA_OK(keys.alloc(m)); NGPD_CUDA_OK(keys2.alloc(m));
+    NGPD_CUDA_OK(vals.alloc(m)); NGPD_CUDA_OK(vals2.alloc(m));
     int rc = point_keys(G->v, query, m, keys, vals, stream);
     if (rc) return rc;
     bool in_tmp = false;
     rc = radix_sort_pairs(keys, vals, keys2, vals2, m, key_bits(G->v), stream, &in_tmp);
     if (rc) return rc;
-    order_from_vals_kernel<<<(unsigned)cdiv(m, 256), 256, 0, stream>>>(in_tmp ? vals2 : vals, m, *order);
+    order_from_vals_kernel<<<(unsigned)cdiv(m, 256), 256, 0, stream>>>(in_tmp ? vals2.p : vals.p, m, order);
     NGPD_CUDA_OK(cudaGetLastError());
-    cudaFreeAsync(keys, stream); cudaFreeAsync(keys2, stream); cudaFreeAsync(vals, stream); cudaFreeAsync(vals2, stream);
     return 0;
 }
 
@@ -163,9 +203,9 @@ template <int K>
 static int launch_knn_fast(const ngpd_grid* G, const float* query, const int32_t* order, int64_t m, int k, int skip, int32_t* idx, float* d2,
                            cudaStream_t s) {
     // two fail lists (tier 1 -> tier 2 -> exact search) and their counters
-    int32_t* fix = nullptr;
-    NGPD_CUDA_OK(cudaMallocAsync(&fix, (size_t)(2 * m + 2) * sizeof(int32_t), s));
-    int32_t *list1 = fix, *list2 = fix + m, *cnt1 = fix + 2 * m, *cnt2 = fix + 2 * m + 1;
+    StreamBuf<int32_t> fix(s);
+    NGPD_CUDA_OK(fix.alloc((size_t)(2 * m + 2)));
+    int32_t *list1 = fix.p, *list2 = fix.p + m, *cnt1 = fix.p + 2 * m, *cnt2 = fix.p + 2 * m + 1;
     NGPD_CUDA_OK(cudaMemsetAsync(cnt1, 0, 2 * sizeof(int32_t), s));
     knn_fast_kernel<K><<<(unsigned)cdiv(m, KsCfg<1>::THREADS), KsCfg<1>::THREADS, 0, s>>>(G->v, query, order, m, k, skip, idx, d2, list1, cnt1);
     int wide = (int)std::min<int64_t>(cdiv(m, KsCfg<2>::THREADS), (int64_t)num_sms() * 16);
@@ -173,7 +213,6 @@ static int launch_knn_fast(const ngpd_grid* G, const float* query, const int32_t
     int blocks = (int)std::min<int64_t>(cdiv(m, 128), (int64_t)num_sms() * 8);
     knn_fix_kernel<K><<<blocks, 128, 0, s>>>(G->v, query, order, k, skip, idx, d2, list2, cnt2);
     NGPD_CUDA_OK(cudaGetLastError());
-    NGPD_CUDA_OK(cudaFreeAsync(fix, s));
     return 0;
 }
 
@@ -187,8 +226,8 @@ extern "C" __attribute__((visibility("default"))) int ngpd_knn(const ngpd_grid_t
     NGPD_REQUIRE(G && query && idx_out, "ngpd_knn: NULL argument");
     NGPD_REQUIRE(k >= 1 && k <= 64, "ngpd_knn: k must be in [1, 64]");
     if (m <= 0) return 0;
-    int32_t* order = nullptr;
-    int rc = make_query_order(G, query, m, flags, stream, &order);
+    StreamBuf<int32_t> order(stream);
+    int rc = make_query_order(G, query, m, flags, stream, order);
     if (rc) return rc;
     int skip = (flags & NGPD_KNN_SKIP_SELF) ? 1 : 0;
     const bool exact_only = (flags & NGPD_KNN_EXACT_ONLY) != 0;
@@ -200,20 +239,41 @@ extern "C" __attribute__((visibility("default"))) int ngpd_knn(const ngpd_grid_t
     else { if (exact_only) launch_knn<64>(G, query, order, m, k, skip, idx_out, d2_out, stream); else rc = launch_knn_fast<64>(G, query, order, m, k, skip, idx_out, d2_out, stream); }
     if (rc) return rc;
     NGPD_CUDA_OK(cudaGetLastError());
-    if (order) NGPD_CUDA_OK(cudaFreeAsync(order, stream));
+    return 0;
+}
+
+static int nn_sqdist_impl(const ngpd_grid_t* G, const float* query, int64_t m, int flags, float* d2_out, int32_t* idx_out, double* acc4_out,
+                          cudaStream_t stream) {
+    StreamBuf<int32_t> order(stream);
+    int rc = make_query_order(G, query, m, flags, stream, order);
+    if (rc) return rc;
+    const int64_t blocks = cdiv(m, 128);
+    if (acc4_out) {
+        StreamBuf<double> part(stream);
+        NGPD_CUDA_OK(part.alloc((size_t)blocks * 4));
+        nn_sqdist_kernel<true><<<(unsigned)blocks, 128, 0, stream>>>(G->v, query, order, m, d2_out, idx_out, part);
+        nn_reduce_kernel<<<1, 256, 0, stream>>>(part, blocks, acc4_out);
+    } else {
+        nn_sqdist_kernel<false><<<(unsigned)blocks, 128, 0, stream>>>(G->v, query, order, m, d2_out, idx_out, nullptr);
+    }
+    NGPD_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
 extern "C" __attribute__((visibility("default"))) int ngpd_nn_sqdist(const ngpd_grid_t* G, const float* query, int64_t m, int flags,
                               float* d2_out, int32_t* idx_out, void* stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
     NGPD_REQUIRE(G && query, "ngpd_nn_sqdist: NULL argument");
     if (m <= 0) return 0;
-    int32_t* order = nullptr;
-    int rc = make_query_order(G, query, m, flags, stream, &order);
-    if (rc) return rc;
-    nn_sqdist_kernel<<<(unsigned)cdiv(m, 128), 128, 0, stream>>>(G->v, query, order, m, d2_out, idx_out);
-    NGPD_CUDA_OK(cudaGetLastError());
-    if (order) NGPD_CUDA_OK(cudaFreeAsync(order, stream));
-    return 0;
+    return nn_sqdist_impl(G, query, m, flags, d2_out, idx_out, nullptr, (cudaStream_t)stream_);
+}
+
+// the same pass with the reduction the metrics' callers apply fused in (Utils.py:253-295: .mean() of the squared distances for
+// Chamfer / sCD, .max() of the distances for Hausdorff, mean distance / diagonal for PaperDistance): acc4_out (device, 4 doubles)
+// = {sum d2, sum d, max d2, rows}, added up in a fixed order (reproducible); d2_out / idx_out are optional here
+extern "C" __attribute__((visibility("default"))) int ngpd_nn_sqdist_reduce(const ngpd_grid_t* G, const float* query, int64_t m, int flags,
+                                     float* d2_out, int32_t* idx_out, double* acc4_out, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    NGPD_REQUIRE(G && query && acc4_out, "ngpd_nn_sqdist_reduce: NULL argument");
+    if (m <= 0) { NGPD_CUDA_OK(cudaMemsetAsync(acc4_out, 0, 4 * sizeof(double), stream)); return 0; }
+    return nn_sqdist_impl(G, query, m, flags, d2_out, idx_out, acc4_out, stream);
 }

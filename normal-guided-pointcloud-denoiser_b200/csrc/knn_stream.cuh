@@ -38,7 +38,6 @@ namespace ngpd {
 
 constexpr int KS_BATCH = 16;          // keys per lane between two selection rounds
 constexpr int KS_GROUP = 4;           // candidates per inner step (loads in flight); the point array is padded by KS_GROUP
-constexpr int KS_OFFBITS = 6;         // a range slot holds at most 64 points (longer ranges take several slots)
 constexpr unsigned KS_NONE = 0xffffffffu;
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -50,9 +49,15 @@ constexpr unsigned FULL = 0xffffffffu;
 template <int R>
 struct KsCfg {
     static constexpr int ROWS = (2 * R + 1) * (2 * R + 1);
-    static constexpr int SLOTS = 2 * ROWS;                       // a row of 2R+1 <= 8 cells crosses at most one brick boundary
+    // A row of 2R+1 <= 8 cells crosses at most one brick boundary: 2 * ROWS pieces, one range slot per piece unless the piece is
+    // longer than a slot.  R = 1: 64-point slots, 18 of them.  R = 2: 128-point slots and 64 of them instead of 50 -- where two
+    // sheets of a surface meet (ncu round 2: the rows around the torus / cube-face intersection of the bench cloud) or with
+    // k = 64 on cells sized for k <= 32, rows of 5 cells hold more than 64 points and 50 slots overflowed, which sent those
+    // queries to the one-thread-per-query exact search (0.8 ms of latency per iteration for a few dozen rows).
+    static constexpr int OFFBITS = R == 1 ? 6 : 7;
+    static constexpr int SLOTS = R == 1 ? 2 * ROWS : 64;
     static constexpr int SLOTBITS = R == 1 ? 5 : 6;
-    static constexpr int IDBITS = SLOTBITS + KS_OFFBITS;
+    static constexpr int IDBITS = SLOTBITS + OFFBITS;
     static constexpr unsigned IDMASK = (1u << IDBITS) - 1u;
     static constexpr int THREADS = R == 1 ? 128 : 64;
     static constexpr double UNIT = 1.0 / (double)(1 << (18 - (IDBITS - 9)));   // of the distance field, in h^2
@@ -141,8 +146,8 @@ __device__ __forceinline__ bool knn_stream(KsTop<KT>& t, KsShared<R>& sm, const 
                     const int* f = g.fine + (int64_t)b * 513 + lrow;
                     int s = __ldg(f + (x0 & 7));
                     const int e = __ldg(f + (xe & 7) + 1);
-                    while (s < e) {                                    // one slot per 64 points
-                        const int ee = min(e, s + (1 << KS_OFFBITS));
+                    while (s < e) {                                    // one slot per 2^OFFBITS points
+                        const int ee = min(e, s + (1 << C::OFFBITS));
                         if (nr < C::SLOTS) { sm.rng[nr][tid] = make_int2(s, ee); ++nr; } else over = true;
                         s = ee;
                     }
@@ -182,7 +187,7 @@ __device__ __forceinline__ bool knn_stream(KsTop<KT>& t, KsShared<R>& sm, const 
         }
         rem -= KS_GROUP;
         if (rem > 0) { pp += KS_GROUP; idv += KS_GROUP; }
-        else if (r < nr) { int2 q = sm.rng[r][tid]; pp = g.pts + q.x; rem = q.y - q.x; idv = (unsigned)r << KS_OFFBITS; ++r; }
+        else if (r < nr) { int2 q = sm.rng[r][tid]; pp = g.pts + q.x; rem = q.y - q.x; idv = (unsigned)r << C::OFFBITS; ++r; }
         else { pp = g.pts; rem = 0; }                                   // done: keep the speculative loads in bounds
         if (__any_sync(FULL, bp > b0 + (KS_BATCH - KS_GROUP) * C::THREADS)) {
             ks_round<KT, R>(t, sm, (int)(bp - b0) / C::THREADS, rej);
@@ -196,8 +201,8 @@ __device__ __forceinline__ bool knn_stream(KsTop<KT>& t, KsShared<R>& sm, const 
 #pragma unroll
     for (int a = 0; a < KT; ++a) {
         const unsigned bits = t.key[a];
-        int slot = min((int)((bits & C::IDMASK) >> KS_OFFBITS), C::SLOTS - 1);
-        t.id[a] = bits != KS_NONE ? sm.rng[slot][tid].x + (int)(bits & ((1u << KS_OFFBITS) - 1u)) : -1;
+        int slot = min((int)((bits & C::IDMASK) >> C::OFFBITS), C::SLOTS - 1);
+        t.id[a] = bits != KS_NONE ? sm.rng[slot][tid].x + (int)(bits & ((1u << C::OFFBITS) - 1u)) : -1;
     }
     if (rlim_out) *rlim_out = 0.0f;
     if (!active || over) return false;

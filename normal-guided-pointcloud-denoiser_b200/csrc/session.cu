@@ -58,12 +58,14 @@ struct ngpd_session {
     int32_t* cand = nullptr;  // [n * 2 * cand_k]
     float4* anchor = nullptr; // [n]
     int cand_k = 0;           // 0 = nothing stored
+    int cand_cap_k = 0;       // row template the candidate rows are allocated (and zero-filled) for
     bool use_rerank = true;
-    double* acc = nullptr;    // 4 doubles
+    double* acc = nullptr;    // 4 x 8 bytes: {sum x, sum y, sum z (fixed point, int64), count (int64)} of flat_step's centre; doubles for the edge lengths
     // flat_step's neighbour sums of class 0, produced by the stage-2 kernel itself when class 0 moves first with the flat
     // strategy: one {sum x, sum y, sum z, count} per block, reduced in a fixed order (no atomics: reproducible)
-    double* part = nullptr;   // [cdiv(n,128) * 4]
-    double* red2 = nullptr;   // scratch of the fixed-order reduction (slice sums + ticket counter)
+    long long* part = nullptr;  // [cdiv(n,128) * 4], fixed point (sum_scale)
+    float sum_scale = 1.0f;     // power of two: a row's neighbour-position sum times this is < 2^32 in magnitude
+    double* red2 = nullptr;     // scratch of the two-level reduction (slice sums + ticket counter)
     bool sums_ready = false;  // part[] describes the current positions and labels
     // rows of classes 1 and 2 (the minorities: creases and corners), listed by the stage-2 kernel so that their updates
     // touch only their own rows instead of streaming the whole cloud through once more: [2 * n rows][2 counters]
@@ -101,6 +103,11 @@ struct ngpd_session {
     int64_t slab_n_send = 0, slab_n_recv = 0;
     unsigned long long slab_epoch = 0;         // one per cross-rank round, the same sequence on every rank
     unsigned* slab_done = nullptr;             // block counter of the export kernel
+    // the last position refresh of a step is only half done when the step returns: the rows are pushed, the wait + scatter is left
+    // for the moment somebody needs halo positions -- the next step's search does not, so it overlaps the exchange
+    bool slab_pull_pending = false;
+    float4* slab_pull_dst = nullptr;
+    unsigned long long slab_pull_epoch = 0;
     float* halo_need = nullptr;                // max over the owned rows of (k-th neighbour distance + distance moved from the tree position)
 };
 
@@ -373,41 +380,60 @@ __global__ void __launch_bounds__(128) session_nvt_smooth_late_kernel(Quad4 pos,
 // stage 2: filtered NVT on the smoothed normals, label + crease direction out.  With part != nullptr the kernel also
 // leaves, per block, {sum x, sum y, sum z, count} over the first ku neighbours of the rows it labelled sum_key
 // (flat_step's centre, Denoiser.py:106): the positions were just gathered, so the separate pass over the class is saved.
-template <int K>
+// FAST: labels from closed-form eigenvalues, crease direction by cross products (eig3_fast.cuh); rows whose label is not certain
+// that way, and every row when FAST is off (a strategy applies edge_step to class 0 or 2, whose smallest eigenvalue is not
+// simple), go through the LAPACK-order solver.  edge_mask: bit l set = rows labelled l need their crease direction stored.
+template <int K, bool FAST>
 __global__ void __launch_bounds__(128, K == 16 ? 9 : (K == 32 ? 6 : 1)) session_nvt_classify_kernel(Quad4 pos, Quad4 fn, const uint8_t* __restrict__ owned,
                                                                    const int32_t* __restrict__ idx, int64_t n, int k, float x_thresh,
-                                                                   float scale, uint8_t* __restrict__ label, float4* __restrict__ edge,
-                                                                   int sum_key, int ku, double* __restrict__ part, int32_t* __restrict__ cls) {
+                                                                   float scale, uint8_t* __restrict__ label, float4* __restrict__ edge, int edge_mask,
+                                                                   int sum_key, int ku, long long* __restrict__ part, float sum_scale,
+                                                                   int32_t* __restrict__ cls) {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = s < n && (!owned || owned[s]);
     float fx = 0.0f, fy = 0.0f, fz = 0.0f;
     int lab = -1;
     if (active) {
-        NvtResult o;
         // the sum of the first ku neighbour positions (flat_step's centre) is accumulated inside the vote loop, where the
         // positions are in registers anyway: fp32 within the row and the warp (the reference's own mean is fp32), fp64 above
         V3 ps = v3(0.0f, 0.0f, 0.0f);
+        float t6[6];
         if (K > 0) {
             RowRegs<K> row;
             row.load(idx + s * K);
-            nvt_point_row<K>(pos, fn, s, row, idx + s * K, K, x_thresh, o, nullptr, part ? &ps : nullptr, ku);
+            nvt_tensor_row<K>(pos, fn, s, row, idx + s * K, K, x_thresh, t6, part ? &ps : nullptr, ku);
         } else {
-            nvt_point_row<0>(pos, fn, s, RowPtr<int32_t>{idx + s * k}, idx + s * k, k, x_thresh, o, nullptr, part ? &ps : nullptr, ku);
+            nvt_tensor_row<0>(pos, fn, s, RowPtr<int32_t>{idx + s * k}, idx + s * k, k, x_thresh, t6, part ? &ps : nullptr, ku);
         }
-        lab = classify(o.w, scale);
-        if (lab == sum_key) { fx = ps.x; fy = ps.y; fz = ps.z; }
+        V3 y = v3(0.0f, 0.0f, 0.0f);
+        bool full = !FAST;
+        if (FAST) {
+            const FastLabel f = classify_fast(t6[0], t6[1], t6[2], t6[3], t6[4], t6[5], scale);
+            lab = f.label;
+            full = !f.certain;
+            if (!full && ((edge_mask >> lab) & 1)) y = eigvec_of(t6[0], t6[1], t6[2], t6[3], t6[4], t6[5], f.l3);
+        }
+        if (full) {
+            const LabelVec o = classify_lapack(t6[0], t6[1], t6[2], t6[3], t6[4], t6[5], scale);
+            lab = o.label; y = o.y;
+        }
+        if (lab == sum_key) { fx = ps.x; fy = ps.y; fz = ps.z; }   // (the row's fp32 sum in neighbour order: the same bits on any partition)
         label[s] = (uint8_t)lab;
-        edge[s] = make_float4(o.V[0], o.V[3], o.V[6], 0.0f);
+        if ((edge_mask >> lab) & 1) edge[s] = make_float4(y.x, y.y, y.z, 0.0f);
     }
     if (part) {
-        __shared__ double red[4][4];
+        // Above the row everything is integer: the row sums in fixed point (sum_scale = a power of two chosen from the cloud's
+        // extent, <= 2^32 per row), so that the total does not depend on which rows share a warp, a block or a GPU -- with fp32
+        // warp sums the centre's last bit, and through delta a few positions' last bits, changed with the partition.
+        __shared__ long long red[4][4];
         const unsigned members = __ballot_sync(0xffffffffu, lab == sum_key);
+        long long qx = __float2ll_rn(fx * sum_scale), qy = __float2ll_rn(fy * sum_scale), qz = __float2ll_rn(fz * sum_scale);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            fx += __shfl_xor_sync(0xffffffffu, fx, o); fy += __shfl_xor_sync(0xffffffffu, fy, o); fz += __shfl_xor_sync(0xffffffffu, fz, o);
+            qx += __shfl_xor_sync(0xffffffffu, qx, o); qy += __shfl_xor_sync(0xffffffffu, qy, o); qz += __shfl_xor_sync(0xffffffffu, qz, o);
         }
         const int w = threadIdx.x >> 5;
-        if ((threadIdx.x & 31) == 0) { red[w][0] = fx; red[w][1] = fy; red[w][2] = fz; red[w][3] = (double)(ku * __popc(members)); }
+        if ((threadIdx.x & 31) == 0) { red[w][0] = qx; red[w][1] = qy; red[w][2] = qz; red[w][3] = (long long)ku * __popc(members); }
         __syncthreads();
         if (threadIdx.x < 4)
             part[(int64_t)blockIdx.x * 4 + threadIdx.x] = ((red[0][threadIdx.x] + red[1][threadIdx.x]) + red[2][threadIdx.x]) + red[3][threadIdx.x];
@@ -438,16 +464,17 @@ __global__ void __launch_bounds__(128, K == 16 ? 9 : (K == 32 ? 6 : 1)) session_
 // slice (fixed order inside the slice), the block that finishes last adds the slice sums in slice order.  Which block
 // that is varies, the order of the additions does not: the result is reproducible.  scratch = RED_BLOCKS*4 doubles + a counter.
 constexpr int RED_BLOCKS = 64;
-__global__ void __launch_bounds__(256) session_partial_reduce_kernel(const double* __restrict__ part, int64_t blocks, double* __restrict__ scratch,
-                                                                     double* __restrict__ acc) {
-    __shared__ double red[8][4];
+// T = double (edge lengths) or long long (flat_step's fixed-point sums: exact, any order)
+template <class T>
+__global__ void __launch_bounds__(256) session_partial_reduce_kernel(const T* __restrict__ part, int64_t blocks, T* __restrict__ scratch,
+                                                                     T* __restrict__ acc) {
+    __shared__ T red[8][4];
     __shared__ bool last;
     const int64_t per = (blocks + RED_BLOCKS - 1) / RED_BLOCKS, b0 = blockIdx.x * per, b1 = b0 + per < blocks ? b0 + per : blocks;
-    double v[4] = {0, 0, 0, 0};
+    T v[4] = {0, 0, 0, 0};
     for (int64_t b = b0 + threadIdx.x; b < b1; b += 256) {
-        const double2* p2 = reinterpret_cast<const double2*>(part + b * 4);
-        double2 lo = p2[0], hi = p2[1];
-        v[0] += lo.x; v[1] += lo.y; v[2] += hi.x; v[3] += hi.y;
+        const T* p4 = part + b * 4;
+        v[0] += p4[0]; v[1] += p4[1]; v[2] += p4[2]; v[3] += p4[3];
     }
 #pragma unroll
     for (int c = 0; c < 4; ++c)
@@ -459,7 +486,7 @@ __global__ void __launch_bounds__(256) session_partial_reduce_kernel(const doubl
     __syncthreads();
     unsigned* counter = reinterpret_cast<unsigned*>(scratch + RED_BLOCKS * 4);
     if (threadIdx.x < 4) {
-        double t = 0;
+        T t = 0;
         for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
         scratch[blockIdx.x * 4 + threadIdx.x] = t;
         __threadfence();
@@ -469,22 +496,25 @@ __global__ void __launch_bounds__(256) session_partial_reduce_kernel(const doubl
     __syncthreads();
     if (last && threadIdx.x < 4) {
         __threadfence();
-        double t = 0;
-        for (int b = 0; b < RED_BLOCKS; ++b) t += *((volatile double*)(scratch + b * 4 + threadIdx.x));
+        T t = 0;
+        for (int b = 0; b < RED_BLOCKS; ++b) t += *((volatile T*)(scratch + b * 4 + threadIdx.x));
         acc[threadIdx.x] = t;
         if (threadIdx.x == 0) *counter = 0;
     }
 }
 
-// flat_step scalars over the neighbour multiset of one class (Denoiser.py:106-107)
+// flat_step scalars over the neighbour multiset of one class (Denoiser.py:106-107): per row the fp32 sum of its first ku neighbour
+// positions in neighbour order (as the stage-2 kernel accumulates it), in fixed point above the row
 __global__ void __launch_bounds__(256) session_class_sum_kernel(Quad4 pos, const uint8_t* __restrict__ owned, const uint8_t* __restrict__ label,
                                                                 int key, const int32_t* __restrict__ idx, int64_t n, int k, int ku,
-                                                                double* __restrict__ part) {
-    double sx = 0, sy = 0, sz = 0, cnt = 0;
+                                                                long long* __restrict__ part, float sum_scale) {
+    long long sx = 0, sy = 0, sz = 0, cnt = 0;
     for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += (int64_t)gridDim.x * blockDim.x) {
         if ((owned && !owned[s]) || label[s] != key) continue;
         const int32_t* row = idx + s * k;
-        for (int a = 0; a < ku; ++a) { V3 p = pos((int64_t)row[a]); sx += p.x; sy += p.y; sz += p.z; }
+        V3 ps = v3(0.0f, 0.0f, 0.0f);
+        for (int a = 0; a < ku; ++a) ps = ps + pos((int64_t)row[a]);
+        sx += __float2ll_rn(ps.x * sum_scale); sy += __float2ll_rn(ps.y * sum_scale); sz += __float2ll_rn(ps.z * sum_scale);
         cnt += ku;
     }
 #pragma unroll
@@ -492,20 +522,20 @@ __global__ void __launch_bounds__(256) session_class_sum_kernel(Quad4 pos, const
         sx += __shfl_xor_sync(0xffffffffu, sx, o); sy += __shfl_xor_sync(0xffffffffu, sy, o);
         sz += __shfl_xor_sync(0xffffffffu, sz, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     }
-    // per-block partial sums, added up in a fixed order by session_partial_reduce_kernel (reproducible, no atomics)
-    __shared__ double red[8][4];
+    __shared__ long long red[8][4];
     const int w = threadIdx.x >> 5;
     if ((threadIdx.x & 31) == 0) { red[w][0] = sx; red[w][1] = sy; red[w][2] = sz; red[w][3] = cnt; }
     __syncthreads();
     if (threadIdx.x < 4) {
-        double t = 0;
+        long long t = 0;
         for (int v = 0; v < 8; ++v) t += red[v][threadIdx.x];
         part[(int64_t)blockIdx.x * 4 + threadIdx.x] = t;
     }
 }
-__global__ void session_center_kernel(const double* __restrict__ acc, float* __restrict__ cd) {
-    double c = acc[3] > 0 ? acc[3] : 1.0;
-    cd[0] = (float)(acc[0] / c); cd[1] = (float)(acc[1] / c); cd[2] = (float)(acc[2] / c); cd[3] = 0.0f;
+// acc = {sum x, sum y, sum z in units of 1 / sum_scale, neighbour count} -> centre
+__global__ void session_center_kernel(const long long* __restrict__ acc, float sum_scale, float* __restrict__ cd) {
+    const double c = acc[3] > 0 ? (double)acc[3] * (double)sum_scale : 1.0;
+    cd[0] = (float)((double)acc[0] / c); cd[1] = (float)((double)acc[1] / c); cd[2] = (float)((double)acc[2] / c); cd[3] = 0.0f;
 }
 __global__ void __launch_bounds__(256) session_class_max_kernel(Quad4 pos, const uint8_t* __restrict__ owned, const uint8_t* __restrict__ label,
                                                                 int key, const int32_t* __restrict__ idx, int64_t n, int k, int ku,
@@ -727,6 +757,7 @@ __global__ void __launch_bounds__(256) slab_pull_kernel(SlabDev d, float4* __res
 // rank order on every rank: identical bits everywhere); mode 1: cd[3] <- max over ranks.  One warp.
 __global__ void __launch_bounds__(32) slab_allreduce_kernel(SlabDev d, double* __restrict__ acc, float* __restrict__ cd, int mode, int parity,
                                                             unsigned long long epoch) {
+    // (mode 0 moves the four 8-byte words bit for bit and adds them as the integers they are: flat_step's fixed-point sums)
     const int q = threadIdx.x;
     double v[4];
     if (mode == 0) { v[0] = acc[0]; v[1] = acc[1]; v[2] = acc[2]; v[3] = acc[3]; }
@@ -744,7 +775,12 @@ __global__ void __launch_bounds__(32) slab_allreduce_kernel(SlabDev d, double* _
     __syncwarp();
     const volatile double* mine = d.scal(d.rank, parity);
     if (mode == 0) {
-        if (q < 4) { double t = 0.0; for (int r = 0; r < d.world; ++r) t += mine[r * 4 + q]; acc[q] = t; }
+        if (q < 4) {
+            const volatile long long* mi = reinterpret_cast<const volatile long long*>(mine);
+            long long t = 0;
+            for (int r = 0; r < d.world; ++r) t += mi[r * 4 + q];
+            reinterpret_cast<long long*>(acc)[q] = t;
+        }
     } else if (q == 0) {
         double t = mine[0];
         for (int r = 1; r < d.world; ++r) t = fmax(t, mine[r * 4]);
@@ -845,6 +881,20 @@ static void run_knn_tiers(ngpd_session* S, int k, int32_t* idx, cudaStream_t st,
     }
 }
 
+// candidate rows + anchors of the re-ranking tier for row template K, zero-filled (rows never searched -- halo -- stay valid ids,
+// anchor radius 0 = nothing stored)
+static int reserve_candidates(ngpd_session* S, int K, cudaStream_t st) {
+    if (S->cand_cap_k == K && S->cand_k == 0) return 0;       // reserved and untouched
+    if (S->cand && S->cand_cap_k != K) { cudaFree(S->cand); S->cand = nullptr; S->cand_cap_k = 0; }
+    S->cand_k = 0;
+    if (!S->cand) NGPD_CUDA_OK(cudaMalloc(&S->cand, (size_t)S->n * 2 * K * sizeof(int32_t)));
+    S->cand_cap_k = K;
+    NGPD_CUDA_OK(cudaMemsetAsync(S->cand, 0, (size_t)S->n * 2 * K * sizeof(int32_t), st));
+    if (!S->anchor) NGPD_CUDA_OK(cudaMalloc(&S->anchor, (size_t)S->n * sizeof(float4)));
+    NGPD_CUDA_OK(cudaMemsetAsync(S->anchor, 0, (size_t)S->n * sizeof(float4), st));
+    return 0;
+}
+
 // `track`: this is the step's own search -- it may answer from, and refreshes, the stored candidates
 template <int K>
 static int run_knn_fast(ngpd_session* S, int k, int32_t* idx, cudaStream_t st, bool track) {
@@ -854,13 +904,9 @@ static int run_knn_fast(ngpd_session* S, int k, int32_t* idx, cudaStream_t st, b
     constexpr bool CAN_TRACK = K <= 32;                      // 2K keys per lane must stay in registers (K = 32: 64 keys, 128 registers, 4 blocks per SM)
     const bool rerank_ok = S->use_rerank && CAN_TRACK;
     if (track && rerank_ok && S->cand_k != K) {
-        // first search with this row length: (re)allocate the candidate rows, no anchors yet
-        if (S->cand) cudaFree(S->cand);
-        S->cand = nullptr; S->cand_k = 0;
-        NGPD_CUDA_OK(cudaMalloc(&S->cand, (size_t)S->n * 2 * K * sizeof(int32_t)));
-        NGPD_CUDA_OK(cudaMemsetAsync(S->cand, 0, (size_t)S->n * 2 * K * sizeof(int32_t), st));   // rows never searched (halo) stay valid ids
-        if (!S->anchor) NGPD_CUDA_OK(cudaMalloc(&S->anchor, (size_t)S->n * sizeof(float4)));
-        NGPD_CUDA_OK(cudaMemsetAsync(S->anchor, 0, (size_t)S->n * sizeof(float4), st));
+        // first search with this row length: candidate rows (allocated here unless ngpd_session_reserve did), no anchors yet
+        int rc = reserve_candidates(S, K, st);
+        if (rc) return rc;
         run_knn_tiers<K, CAN_TRACK ? 2 * K : K>(S, k, idx, st, false);
         S->cand_k = K;
         S->knn_launches = 3;
@@ -911,6 +957,10 @@ static int run_knn(ngpd_session* S, int k, int32_t* idx, cudaStream_t st, bool t
 
 using namespace ngpd;
 
+// completes a halo refresh whose second half (wait + scatter) was deferred; defined with the slab code below.  Every entry that
+// reads or replaces positions of halo rows, or starts another cross-rank round, calls it first.
+static int slab_flush(ngpd_session_t* S, cudaStream_t st);
+
 extern "C" __attribute__((visibility("default"))) int ngpd_session_destroy(ngpd_session_t* S) {
     if (!S) return 0;
     if (S->grid) ngpd_grid_destroy(S->grid);
@@ -935,6 +985,15 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_create(const 
     if (rc) return rc;
     ngpd_session* S = new ngpd_session();
     S->grid = G; S->n = n;
+    {
+        // fixed-point unit of flat_step's centre sums: a row adds up to 64 neighbour positions, positions may drift to twice the
+        // tree's extent -> |row sum| <= 128 max|coordinate|, mapped below 2^32 (2^31 rows then still fit 63 bits)
+        float maxabs = 0.0f;
+        for (int c = 0; c < 6; ++c) maxabs = std::max(maxabs, std::fabs(G->bbox[c]));
+        int e = 0;
+        std::frexp(128.0 * (double)std::max(maxabs, 1e-30f), &e);      // 128 maxabs < 2^e
+        S->sum_scale = std::ldexp(1.0f, std::max(-100, std::min(100, 32 - e)));
+    }
     size_t b4 = (size_t)n * sizeof(float4);
     cudaError_t e = cudaSuccess;
     if (e == cudaSuccess) e = cudaMalloc(&S->pos[0], b4);
@@ -960,6 +1019,7 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_create(const 
 
 extern "C" __attribute__((visibility("default"))) int ngpd_session_set_state(ngpd_session_t* S, const float* pos, const float* nrm, void* stream_) {
     NGPD_REQUIRE(S, "ngpd_session_set_state: NULL session");
+    { int rc = slab_flush(S, (cudaStream_t)stream_); if (rc) return rc; }
     S->sums_ready = false;
     // (positions replaced from outside keep the stored kNN candidates usable: tier 0 measures the displacement from the anchor)
     session_scatter_in_kernel<<<(unsigned)cdiv(S->n, 256), 256, 0, (cudaStream_t)stream_>>>(S->grid->pts, pos, nrm, S->n, S->pos[S->cur], S->nrm);
@@ -969,6 +1029,7 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_set_state(ngp
 
 extern "C" __attribute__((visibility("default"))) int ngpd_session_get_state(ngpd_session_t* S, float* pos_out, float* nrm_out, uint8_t* labels_out, void* stream_) {
     NGPD_REQUIRE(S, "ngpd_session_get_state: NULL session");
+    { int rc = slab_flush(S, (cudaStream_t)stream_); if (rc) return rc; }
     if (!S->inv) {
         NGPD_CUDA_OK(cudaMalloc(&S->inv, (size_t)S->n * sizeof(int32_t)));
         session_inverse_kernel<<<(unsigned)cdiv(S->n, 256), 256, 0, (cudaStream_t)stream_>>>(S->grid->pts, S->n, S->inv);
@@ -1000,6 +1061,35 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_order(const n
 
 extern "C" __attribute__((visibility("default"))) int ngpd_session_launch_count(const ngpd_session_t* S) { return S ? S->launches : 0; }
 
+static int ensure_tail(ngpd_session_t* S, cudaStream_t st) {
+    if (S->tail) return 0;
+    // highest priority: its few blocks must get SM slots as the tensor pass' blocks retire, not after all of them
+    int prio_lo = 0, prio_hi = 0;
+    NGPD_CUDA_OK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    NGPD_CUDA_OK(cudaStreamCreateWithPriority(&S->tail, cudaStreamNonBlocking, prio_hi));
+    for (cudaEvent_t& e : S->tail_ev) NGPD_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    NGPD_CUDA_OK(cudaMalloc(&S->late, (size_t)S->n));
+    NGPD_CUDA_OK(cudaMemsetAsync(S->late, 0, (size_t)S->n, st));
+    return 0;
+}
+
+// Everything a step with neighbourhood size k_feature allocates on first use (neighbour table, candidate rows of the re-ranking
+// tier, class lists, partial sums, side stream) now, so that the first iteration of a run costs what its kernels cost.
+extern "C" __attribute__((visibility("default"))) int ngpd_session_reserve(ngpd_session_t* S, int k_feature, void* stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    NGPD_REQUIRE(S && k_feature >= 1 && k_feature <= 64, "ngpd_session_reserve: bad argument");
+    int rc = ensure_idx(S, k_feature);
+    if (rc) return rc;
+    if ((rc = ensure_tail(S, st))) return rc;
+    if (S->use_rerank && k_feature > 4 && k_feature <= 32 && S->cand_k == 0) {
+        const int K = k_feature <= 8 ? 8 : (k_feature <= 16 ? 16 : 32);
+        if ((rc = reserve_candidates(S, K, st))) return rc;
+    }
+    if (!S->part) NGPD_CUDA_OK(cudaMalloc(&S->part, (size_t)cdiv(S->n, 128) * 4 * sizeof(long long)));
+    if (!S->cls) NGPD_CUDA_OK(cudaMalloc(&S->cls, (2 * (size_t)S->n + 2) * sizeof(int32_t)));
+    return 0;
+}
+
 // ---- phases (exposed one by one so that a multi-GPU driver can exchange halos in between) -----------
 // part 0 of the feature phase in its two halves (the host-buffer entry point overlaps transfers with each of them)
 static int features_knn(ngpd_session_t* S, const ngpd_step_params_t* p, cudaStream_t st) {
@@ -1007,15 +1097,7 @@ static int features_knn(ngpd_session_t* S, const ngpd_step_params_t* p, cudaStre
     int rc = ensure_idx(S, kf);
     if (rc) return rc;
     S->idx_k = kf;
-    if (!S->tail) {
-        // highest priority: its few blocks must get SM slots as the tensor pass' blocks retire, not after all of them
-        int prio_lo = 0, prio_hi = 0;
-        NGPD_CUDA_OK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-        NGPD_CUDA_OK(cudaStreamCreateWithPriority(&S->tail, cudaStreamNonBlocking, prio_hi));
-        for (cudaEvent_t& e : S->tail_ev) NGPD_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        NGPD_CUDA_OK(cudaMalloc(&S->late, (size_t)S->n));
-        NGPD_CUDA_OK(cudaMemsetAsync(S->late, 0, (size_t)S->n, st));
-    }
+    if ((rc = ensure_tail(S, st))) return rc;
     static const bool tail_off = getenv("NGPD_NO_TAIL_OVERLAP") != nullptr;   // measurements only
     S->overlap_tail = !tail_off;   // honoured by the tiered search only (5 <= k <= 32, not in exact-only mode)
     { ProfScope ps(S, st, 0); rc = run_knn(S, kf, S->idx, st, true); }
@@ -1061,14 +1143,17 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_phase_feature
     unsigned b = (unsigned)cdiv(S->n, 128);
     Quad4 pos{S->pos[S->cur]};
     if (part == 0) {
+        // (the search reads the queries' own rows only: a deferred halo refresh of the positions completes behind it)
         int rc = features_knn(S, p, st);
+        if (!rc) rc = slab_flush(S, st);
         if (!rc) rc = features_smooth(S, p, st);
         if (rc) return rc;
     } else {
+        { int rc = slab_flush(S, st); if (rc) return rc; }
         // class 0 moves first: when it uses the flat strategy its neighbour sums come out of this kernel
-        double* part = nullptr;
+        long long* part = nullptr;
         if (p->strategy[0] == NGPD_STEP_FLAT) {
-            if (!S->part) NGPD_CUDA_OK(cudaMalloc(&S->part, (size_t)b * 4 * sizeof(double)));
+            if (!S->part) NGPD_CUDA_OK(cudaMalloc(&S->part, (size_t)b * 4 * sizeof(long long)));
             part = S->part;
         }
         S->sums_ready = part != nullptr;
@@ -1076,12 +1161,22 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_phase_feature
         int32_t* cls = S->cls;
         NGPD_CUDA_OK(cudaMemsetAsync(cls + 2 * S->n, 0, 2 * sizeof(int32_t), st));
         S->lists_ready = true;
+        // which labels' rows need their crease direction (edge_step's y, Processor.py:134); the closed-form stage-2 path serves
+        // the default strategies, a strategy with edge_step on class 0 or 2 keeps the LAPACK-order vectors for every row
+        int edge_mask = 0;
+        for (int key = 0; key < 3; ++key) if (p->strategy[key] == NGPD_STEP_EDGE) edge_mask |= 1 << key;
+        static const bool fast_off = getenv("NGPD_NO_FAST_LABELS") != nullptr;   // measurements / A-B tests only
+        const bool fast = !fast_off && (edge_mask & ~2) == 0;
         { ProfScope ps(S, st, 2);
           Quad4 fq{S->fn};
-          if (kf == 16) session_nvt_classify_kernel<16><<<b, 128, 0, st>>>(pos, fq, S->owned, S->idx, S->n, kf, p->x_thresh, p->scale, S->label, S->edge, 0, p->k_update, part, cls);
-          else if (kf == 32) session_nvt_classify_kernel<32><<<b, 128, 0, st>>>(pos, fq, S->owned, S->idx, S->n, kf, p->x_thresh, p->scale, S->label, S->edge, 0, p->k_update, part, cls);
-          else if (kf == 8) session_nvt_classify_kernel<8><<<b, 128, 0, st>>>(pos, fq, S->owned, S->idx, S->n, kf, p->x_thresh, p->scale, S->label, S->edge, 0, p->k_update, part, cls);
-          else session_nvt_classify_kernel<0><<<b, 128, 0, st>>>(pos, fq, S->owned, S->idx, S->n, kf, p->x_thresh, p->scale, S->label, S->edge, 0, p->k_update, part, cls); }
+#define NGPD_CLASSIFY(KK, FF) session_nvt_classify_kernel<KK, FF><<<b, 128, 0, st>>>(pos, fq, S->owned, S->idx, S->n, kf, p->x_thresh, p->scale, S->label, S->edge, edge_mask, 0, p->k_update, part, S->sum_scale, cls)
+          if (fast) {
+              if (kf == 16) NGPD_CLASSIFY(16, true); else if (kf == 32) NGPD_CLASSIFY(32, true); else if (kf == 8) NGPD_CLASSIFY(8, true); else NGPD_CLASSIFY(0, true);
+          } else {
+              if (kf == 16) NGPD_CLASSIFY(16, false); else if (kf == 32) NGPD_CLASSIFY(32, false); else if (kf == 8) NGPD_CLASSIFY(8, false); else NGPD_CLASSIFY(0, false);
+          }
+#undef NGPD_CLASSIFY
+        }
         S->launches += 1;
     }
     NGPD_CUDA_OK(cudaGetLastError());
@@ -1094,21 +1189,24 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_phase_feature
 extern "C" __attribute__((visibility("default"))) int ngpd_session_phase_flat_scalars(ngpd_session_t* S, const ngpd_step_params_t* p, int key, int part, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     NGPD_REQUIRE(S && p, "ngpd_session_phase_flat_scalars: NULL argument");
+    { int rc = slab_flush(S, st); if (rc) return rc; }
     // (snapshot mode: classes 1 and 2 still read the positions class 0's pass started from)
     Quad4 pos{S->pos[((p->flags & NGPD_STEP_SNAPSHOT_CLASSES) && key > 0) ? S->cur ^ 1 : S->cur]};
     ProfScope ps(S, st, 3);
     if (part == 0 && key == 0 && S->sums_ready) {
-        session_partial_reduce_kernel<<<RED_BLOCKS, 256, 0, st>>>(S->part, cdiv(S->n, 128), S->red2, S->acc);
+        session_partial_reduce_kernel<long long><<<RED_BLOCKS, 256, 0, st>>>(S->part, cdiv(S->n, 128), reinterpret_cast<long long*>(S->red2),
+                                                                             reinterpret_cast<long long*>(S->acc));
         S->launches += 1;
     } else if (part == 0) {
-        if (!S->part) NGPD_CUDA_OK(cudaMalloc(&S->part, (size_t)cdiv(S->n, 128) * 4 * sizeof(double)));
+        if (!S->part) NGPD_CUDA_OK(cudaMalloc(&S->part, (size_t)cdiv(S->n, 128) * 4 * sizeof(long long)));
         const unsigned blocks = strided(S->n, 256);
-        session_class_sum_kernel<<<blocks, 256, 0, st>>>(pos, S->owned, S->label, key, S->idx, S->n, S->idx_k, p->k_update, S->part);
-        session_partial_reduce_kernel<<<RED_BLOCKS, 256, 0, st>>>(S->part, (int64_t)blocks, S->red2, S->acc);
+        session_class_sum_kernel<<<blocks, 256, 0, st>>>(pos, S->owned, S->label, key, S->idx, S->n, S->idx_k, p->k_update, S->part, S->sum_scale);
+        session_partial_reduce_kernel<long long><<<RED_BLOCKS, 256, 0, st>>>(S->part, (int64_t)blocks, reinterpret_cast<long long*>(S->red2),
+                                                                             reinterpret_cast<long long*>(S->acc));
         S->sums_ready = false;
         S->launches += 2;
     } else {
-        session_center_kernel<<<1, 1, 0, st>>>(S->acc, S->cd);
+        session_center_kernel<<<1, 1, 0, st>>>(reinterpret_cast<const long long*>(S->acc), S->sum_scale, S->cd);
         session_class_max_kernel<<<strided(S->n, 256), 256, 0, st>>>(pos, S->owned, S->label, key, S->idx, S->n, S->idx_k, p->k_update, S->cd);
         S->launches += 2;
     }
@@ -1119,6 +1217,7 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_phase_flat_sc
 extern "C" __attribute__((visibility("default"))) int ngpd_session_phase_update(ngpd_session_t* S, const ngpd_step_params_t* p, int key, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     NGPD_REQUIRE(S && p && key >= 0 && key < 3, "ngpd_session_phase_update: bad argument");
+    { int rc = slab_flush(S, st); if (rc) return rc; }
     int kind = p->strategy[key];
     const bool snapshot = (p->flags & NGPD_STEP_SNAPSHOT_CLASSES) != 0;
     // snapshot mode: class 0's pass doubles as the copy of the snapshot into the other buffer, so it runs even when class 0 stays put
@@ -1205,6 +1304,7 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_step(ngpd_ses
 extern "C" __attribute__((visibility("default"))) int ngpd_session_mean_edge_length(ngpd_session_t* S, int k, double* out_host, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     NGPD_REQUIRE(S && out_host && k >= 1 && k <= 64, "ngpd_session_mean_edge_length: bad argument");
+    { int rc = slab_flush(S, st); if (rc) return rc; }
     int32_t* idx = nullptr;
     double *acc = nullptr, *part = nullptr;
     const unsigned blocks = strided(S->n, 256);
@@ -1214,7 +1314,7 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_mean_edge_len
     int rc = run_knn(S, k, idx, st);
     if (rc) return rc;
     session_edge_len_kernel<<<blocks, 256, 0, st>>>(Quad4{S->pos[S->cur]}, S->owned, idx, S->n, k, part);
-    session_partial_reduce_kernel<<<RED_BLOCKS, 256, 0, st>>>(part, (int64_t)blocks, S->red2, acc);
+    session_partial_reduce_kernel<double><<<RED_BLOCKS, 256, 0, st>>>(part, (int64_t)blocks, S->red2, acc);
     double h[2];
     NGPD_CUDA_OK(cudaMemcpyAsync(h, acc, sizeof(h), cudaMemcpyDeviceToHost, st));
     NGPD_CUDA_OK(cudaStreamSynchronize(st));
@@ -1289,6 +1389,7 @@ extern "C" __attribute__((visibility("default"))) void* ngpd_session_buffer(ngpd
 
 extern "C" __attribute__((visibility("default"))) int ngpd_session_export_rows(ngpd_session_t* S, int which, const int32_t* rows, int64_t m, float* out4, void* stream_) {
     NGPD_REQUIRE(S && (which >= 0 && which <= 2), "ngpd_session_export_rows: bad argument");
+    { int rc = slab_flush(S, (cudaStream_t)stream_); if (rc) return rc; }
     if (m <= 0) return 0;
     const float4* src = which == 0 ? S->pos[S->cur] : (which == 1 ? S->nrm : S->fn);
     session_export_kernel<<<(unsigned)cdiv(m, 256), 256, 0, (cudaStream_t)stream_>>>(src, rows, m, (float4*)out4);
@@ -1306,6 +1407,7 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_export_rows_p
 }
 extern "C" __attribute__((visibility("default"))) int ngpd_session_import_rows(ngpd_session_t* S, int which, const int32_t* rows, int64_t m, const float* in4, void* stream_) {
     NGPD_REQUIRE(S && (which >= 0 && which <= 2), "ngpd_session_import_rows: bad argument");
+    { int rc = slab_flush(S, (cudaStream_t)stream_); if (rc) return rc; }
     if (m <= 0) return 0;
     float4* dst = which == 0 ? S->pos[S->cur] : (which == 1 ? S->nrm : S->fn);
     if (which == 0) S->sums_ready = false;
@@ -1323,7 +1425,7 @@ extern "C" __attribute__((visibility("default"))) int64_t ngpd_slab_symm_bytes(i
 
 extern "C" __attribute__((visibility("default"))) int ngpd_session_set_slab(ngpd_session_t* S, const ngpd_slab_wiring_t* w, void* stream_) {
     NGPD_REQUIRE(S, "ngpd_session_set_slab: NULL session");
-    if (!w) { delete S->slab; S->slab = nullptr; return 0; }
+    if (!w) { delete S->slab; S->slab = nullptr; S->slab_pull_pending = false; return 0; }
     NGPD_REQUIRE(w->world >= 1 && w->world <= SLAB_MAX_WORLD && w->rank >= 0 && w->rank < w->world, "ngpd_session_set_slab: bad world / rank");
     NGPD_REQUIRE(w->send_seg_host && w->first_row_host && w->symm_base_host, "ngpd_session_set_slab: NULL table");
     NGPD_REQUIRE((w->n_send == 0 || w->send_rows) && (w->n_recv == 0 || w->recv_rows) && w->n_recv <= w->cap, "ngpd_session_set_slab: bad row lists");
@@ -1336,6 +1438,7 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_set_slab(ngpd
     S->slab_send_rows = w->send_rows; S->slab_recv_rows = w->recv_rows;
     S->slab_n_send = w->n_send; S->slab_n_recv = w->n_recv;
     S->slab_epoch = 0;
+    S->slab_pull_pending = false;
     if (!S->slab_done) {
         NGPD_CUDA_OK(cudaMalloc(&S->slab_done, sizeof(unsigned)));
         NGPD_CUDA_OK(cudaMemsetAsync(S->slab_done, 0, sizeof(unsigned), (cudaStream_t)stream_));
@@ -1345,23 +1448,49 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_set_slab(ngpd
 
 static float4* slab_buffer(ngpd_session_t* S, int which) { return which == 0 ? S->pos[S->cur] : (which == 1 ? S->nrm : S->fn); }
 
+// first half of a refresh: gather + store into the peers' receive buffers + signal
+static int slab_push(ngpd_session_t* S, const float4* buf, unsigned long long* epoch_out, cudaStream_t st) {
+    const SlabDev& d = *S->slab;
+    const unsigned long long epoch = ++S->slab_epoch;
+    // (grids small enough to be resident at once: the pull kernel's blocks wait for the peers)
+    const int pb = stride_blocks(std::max<int64_t>(S->slab_n_send, 1), 256, 4);
+    slab_push_kernel<<<pb, 256, 0, st>>>(d, buf, S->slab_send_rows, S->slab_n_send, (int)(epoch & 1), epoch, S->slab_done);
+    NGPD_CUDA_OK(cudaGetLastError());
+    *epoch_out = epoch;
+    S->launches += 1;
+    return 0;
+}
+// second half: wait for every peer's rows of that round, scatter them into the halo rows
+static int slab_pull(ngpd_session_t* S, float4* buf, unsigned long long epoch, cudaStream_t st) {
+    const SlabDev& d = *S->slab;
+    const int qb = stride_blocks(std::max<int64_t>(S->slab_n_recv, 1), 256, 4);
+    slab_pull_kernel<<<qb, 256, 0, st>>>(d, buf, S->slab_recv_rows, S->slab_n_recv, (int)(epoch & 1), epoch);
+    NGPD_CUDA_OK(cudaGetLastError());
+    S->launches += 1;
+    return 0;
+}
+// complete a refresh whose second half was deferred (must happen before anything reads halo positions, before the next
+// cross-rank round -- a peer may only run one round ahead of what this rank has consumed -- and before positions are replaced)
+static int slab_flush(ngpd_session_t* S, cudaStream_t st) {
+    if (!S->slab_pull_pending) return 0;
+    S->slab_pull_pending = false;
+    ProfScope ps(S, st, 5);
+    return slab_pull(S, S->slab_pull_dst, S->slab_pull_epoch, st);
+}
+
 // one halo refresh of buffer `which` (0 positions, 1 normals, 2 smoothed normals): every rank must call it in the same order
 extern "C" __attribute__((visibility("default"))) int ngpd_session_slab_refresh(ngpd_session_t* S, int which, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     NGPD_REQUIRE(S && S->slab && which >= 0 && which <= 2, "ngpd_session_slab_refresh: no slab wiring / bad buffer");
-    const SlabDev& d = *S->slab;
-    if (d.world == 1) return 0;
+    if (S->slab->world == 1) return 0;
+    int rc = slab_flush(S, st);
+    if (rc) return rc;
     ProfScope ps(S, st, 5);
-    const unsigned long long epoch = ++S->slab_epoch;
-    const int parity = (int)(epoch & 1);
     float4* buf = slab_buffer(S, which);
-    // (grids small enough to be resident at once: the pull kernel's blocks wait for the peers)
-    const int pb = stride_blocks(std::max<int64_t>(S->slab_n_send, 1), 256, 4), qb = stride_blocks(std::max<int64_t>(S->slab_n_recv, 1), 256, 4);
-    slab_push_kernel<<<pb, 256, 0, st>>>(d, buf, S->slab_send_rows, S->slab_n_send, parity, epoch, S->slab_done);
-    slab_pull_kernel<<<qb, 256, 0, st>>>(d, buf, S->slab_recv_rows, S->slab_n_recv, parity, epoch);
-    NGPD_CUDA_OK(cudaGetLastError());
+    unsigned long long epoch = 0;
+    if ((rc = slab_push(S, buf, &epoch, st))) return rc;
+    if ((rc = slab_pull(S, buf, epoch, st))) return rc;
     if (which == 0) S->sums_ready = false;
-    S->launches += 2;
     return 0;
 }
 
@@ -1371,6 +1500,8 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_slab_allreduc
     NGPD_REQUIRE(S && S->slab && (mode == 0 || mode == 1), "ngpd_session_slab_allreduce: no slab wiring / bad mode");
     const SlabDev& d = *S->slab;
     if (d.world == 1) return 0;
+    int rc = slab_flush(S, st);
+    if (rc) return rc;
     ProfScope ps(S, st, 5);
     const unsigned long long epoch = ++S->slab_epoch;
     slab_allreduce_kernel<<<1, 32, 0, st>>>(d, S->acc, S->cd, mode, (int)(epoch & 1), epoch);
@@ -1399,8 +1530,20 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_step_slab(ngp
         if ((rc = ngpd_session_phase_update(S, p, key, stream_))) return rc;
         // the class' new positions, before the next class reads them (snapshot mode: nobody reads them before the step ends)
         const bool moved = p->strategy[key] >= 0;
-        if ((moved && !snapshot) || (snapshot && key == 2))
+        bool later = false;                                  // does a later class still read positions in this step?
+        for (int q = key + 1; q < 3; ++q) later = later || p->strategy[q] >= 0;
+        if ((moved && !snapshot && later) || (snapshot && key == 2 && false))
             if ((rc = ngpd_session_slab_refresh(S, 0, stream_))) return rc;
+    }
+    // the step's last position refresh: pushed now, pulled when the next reader of halo positions comes along (the next step's
+    // search reads owned rows only, so the exchange and the slowest peer's tail hide behind it)
+    if (S->slab->world > 1) {
+        cudaStream_t st = (cudaStream_t)stream_;
+        ProfScope ps(S, st, 5);
+        S->slab_pull_dst = S->pos[S->cur];
+        if ((rc = slab_push(S, S->slab_pull_dst, &S->slab_pull_epoch, st))) return rc;
+        S->slab_pull_pending = true;
+        S->sums_ready = false;
     }
     return ngpd_session_phase_commit_normals(S);
 }
@@ -1423,6 +1566,7 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_halo_need(ngp
 extern "C" __attribute__((visibility("default"))) int ngpd_session_checksum(ngpd_session_t* S, const int64_t* global_ids, uint64_t* out11_host, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     NGPD_REQUIRE(S && out11_host, "ngpd_session_checksum: NULL argument");
+    { int rc = slab_flush(S, st); if (rc) return rc; }
     unsigned long long* d = nullptr;
     NGPD_CUDA_OK(cudaMallocAsync(&d, CHECKSUM_WORDS * sizeof(unsigned long long), st));
     cudaError_t e = cudaMemsetAsync(d, 0, CHECKSUM_WORDS * sizeof(unsigned long long), st);
@@ -1448,6 +1592,7 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_run_host(ngpd
                                      void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     NGPD_REQUIRE(S && p && pos_host && nrm_host, "ngpd_session_run_host: NULL argument");
+    { int rc = slab_flush(S, st); if (rc) return rc; }
     NGPD_REQUIRE(p->k_feature >= 1 && p->k_feature <= 64 && p->k_update >= 1 && p->k_update <= p->k_feature,
                  "ngpd_session: need 1 <= k_update <= k_feature <= 64");
     size_t b3 = (size_t)S->n * 3 * sizeof(float);

@@ -450,7 +450,7 @@ class SlabSession:
         self.session.set_state(None, full)
         self._refresh(1)
 
-    def pca_normals(self, k: int = 12, orient_like: torch.Tensor | None = None) -> torch.Tensor:
+    def pca_normals(self, k: int = 12, orient_like=None) -> torch.Tensor:
         """GraphBuilder.getKNNEdgeIndex(k) + setPVTNormals on the slab (GraphBuilder.py:60-63, 95-111): k-NN graph without
         self over the construction-time positions, PCA normal per owned row, optionally flipped to agree with `orient_like`
         (owned rows); sets them as the session's normals and returns them."""
@@ -462,6 +462,9 @@ class SlabSession:
         with torch.cuda.device(tree.device):
             L.check(L.load().ngpd_pca_normals(tree.data_ptr(), table.data_ptr(), None, self.n_owned, k, nrm.data_ptr(), None, None, L.stream()),
                     "ngpd_pca_normals")
+        if isinstance(orient_like, str):
+            assert orient_like == "current"                     # the normals the session holds now (e.g. analytic ones routed with the shards)
+            orient_like = self.owned_state()[2]
         if orient_like is not None:
             flip = (nrm * orient_like).sum(1) < 0
             nrm[flip] *= -1
@@ -526,7 +529,8 @@ class SlabSession:
     def _views(self):
         # the flat-step accumulators live at fixed addresses for the session's life: wrap them once
         if not hasattr(self, "_scalar_views"):
-            self._scalar_views = (self._scalar_view(3, (4,), "<f8"), self._scalar_view(4, (4,), "<f4")[3:4])
+            # buffer 3: flat_step's centre sums as int64 fixed point (exact: any summation order gives the same bits)
+            self._scalar_views = (self._scalar_view(3, (4,), "<i8"), self._scalar_view(4, (4,), "<f4")[3:4])
         return self._scalar_views
 
     def step(self):
@@ -610,3 +614,78 @@ class SlabSession:
         labels = self._scalar_view(5, (self.n_owned + self.n_halo,), "|u1")
         lab_out.copy_(labels[rows.long()], non_blocking=True)
         torch.cuda.current_stream().synchronize()
+
+
+# ------------------------------------------------------------------------------------------------------
+# sharded metrics and k-NN (BASELINE configs[4] beyond one GPU)
+# ------------------------------------------------------------------------------------------------------
+def _all_gather_rows(t: torch.Tensor, group) -> torch.Tensor:
+    world = dist.get_world_size(group)
+    size = torch.tensor([t.size(0)], dtype=torch.long, device=t.device)
+    sizes = [torch.empty_like(size) for _ in range(world)]
+    dist.all_gather(sizes, size, group=group)
+    sizes = [int(v.item()) for v in sizes]
+    pad = torch.zeros((max(sizes),) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    pad[:t.size(0)] = t
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad, group=group)
+    return torch.cat([b[:m] for b, m in zip(bufs, sizes)])
+
+
+def sharded_chamfer(a_shard: torch.Tensor, b_shard: torch.Tensor, group=None) -> dict:
+    """TorchUtils.ChamferDistance(A, B).mean() and friends (Utils.py:253-295) for clouds spread over the ranks: every rank
+    queries ITS shard of B against a replica of A and its shard of A against a replica of B (a replicated target
+    costs 12 B/point -- 12 GB at 10^9 points -- which a B200 holds), with the block reduction fused into the nearest-
+    neighbour kernel (ngpd_nn_sqdist_reduce: no per-point output), then one all-reduce of 8 doubles.  Returns python floats."""
+    from . import _lib
+    multi = dist.is_initialized() and dist.get_world_size(group) > 1
+    a_full = _all_gather_rows(a_shard, group) if multi else a_shard
+    ga = _lib.Grid(a_full, 4)
+    del a_full
+    acc_b = ga.nn_reduce(b_shard)                               # every B point -> nearest A point (first half of the reference's vector)
+    del ga
+    b_full = _all_gather_rows(b_shard, group) if multi else b_shard
+    gb = _lib.Grid(b_full, 4)
+    del b_full
+    acc_a = gb.nn_reduce(a_shard)
+    del gb
+    sums = torch.stack([acc_b[0], acc_b[1], acc_b[3], acc_a[0], acc_a[1], acc_a[3]])
+    mx = torch.stack([acc_b[2], acc_a[2]])
+    if multi:
+        dist.all_reduce(sums, group=group)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+    s = [float(v) for v in sums.tolist()]
+    return {"chamfer": (s[0] + s[3]) / (s[2] + s[5]), "single_chamfer": s[0] / s[2], "hausdorff": math.sqrt(float(mx.max())),
+            "mean_distance": s[1] / s[2], "rows": int(s[2] + s[5])}
+
+
+class ShardedKnn:
+    """k nearest neighbours of a cloud that is spread over the ranks (Selector.getKNNSelection beyond one GPU): Morton slabs
+    from the shards (ShardedSlabPlan), one index per rank over owned + halo rows, every rank answers its owned rows.  Rows come
+    back as GLOBAL ids.  `check()` proves the rows equal the whole cloud's (k-th distance below the halo width)."""
+
+    def __init__(self, shard_pos: torch.Tensor, shard_ids: torch.Tensor, k_max: int, group=None, halo_width: float | None = None):
+        from . import _lib
+        self._lib, self.group = _lib, group
+        hw = halo_width if halo_width is not None else estimate_halo_width_sharded(shard_pos, k_max, group)
+        self.plan = ShardedSlabPlan(shard_pos, shard_ids, hw, group)
+        self.grid = _lib.Grid(self.plan.tree_local, k_max)
+        self.n_owned = self.plan.n_owned
+        self.queries = self.plan.tree_local[:self.n_owned].contiguous()
+
+    def knn(self, k: int, flags: int = 0, global_ids: bool = True, with_d2: bool = False):
+        out = self.grid.knn(self.queries, k, flags, with_d2=True)
+        idx, d2 = out
+        self._last_dk = d2[:, k - 1].max() if idx.numel() else torch.zeros((), device=idx.device)
+        if global_ids:
+            idx = self.plan.local_ids[idx.long()]
+        return (idx, d2) if with_d2 else idx
+
+    def check(self) -> float:
+        need = self._last_dk.double().sqrt().reshape(1)
+        if dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(need, op=dist.ReduceOp.MAX, group=self.group)
+        need = float(need.item())
+        if not need < self.plan.halo_width:
+            raise RuntimeError(f"halo too narrow: k-th neighbour at {need:.6g}, halo width {self.plan.halo_width:.6g}")
+        return need

@@ -485,14 +485,19 @@ def feature_decomposition(pos, nrm, nbr_f, x_thresh, tau=0.3, damp=3.0):
 
 
 def denoise_iteration(tree, pos, nrm, k_f=16, k_u=8, x_thresh=None, alphas=(1.0, 0.2, 1.0), dmax=None,
-                      strategy=("flat", "edge", "feature"), knn=knn_kdtree, scale=0.2, tau=0.3, damp=3.0):
-    """One body of Processor.denoise (Processor.py:124-139) against the frozen tree `tree`."""
+                      strategy=("flat", "edge", "feature"), knn=knn_kdtree, scale=0.2, tau=0.3, damp=3.0,
+                      snapshot=False, original=None, clamp=None):
+    """One body of Processor.denoise (Processor.py:124-139) against the frozen tree `tree`.
+    snapshot=True + original + clamp: the notebook's variant (PostProcessing.ipynb#c9, "Ours" / "CPSD"): every class reads the
+    positions the iteration started from (results go to temp_pos), and a new position is kept only where
+    |temp_pos - original| < clamp."""
     pos = np.array(pos, dtype=F32, copy=True); nrm = np.asarray(nrm, dtype=F32)
     nbr_f = knn(tree, pos, k_f)
     w2, V2, f, _ = feature_decomposition(pos, nrm, nbr_f, x_thresh, tau, damp)
     lab = classes(w2, scale)
     nbr_u = knn(tree, pos, k_u)
     edge_vec = V2[:, :, 0]
+    src = pos.copy() if snapshot else pos
     for key in range(3):
         rows = np.nonzero(lab == key)[0]
         if len(rows) == 0:
@@ -500,16 +505,19 @@ def denoise_iteration(tree, pos, nrm, k_f=16, k_u=8, x_thresh=None, alphas=(1.0,
         kind = strategy[key]
         sub = nbr_u[rows]
         if kind == "flat":
-            new = flat_step(pos, f, rows, sub, dmax, alphas[key])
+            new = flat_step(src, f, rows, sub, dmax, alphas[key])
         elif kind == "edge":
-            new = edge_step(pos, f, edge_vec, rows, sub, dmax, alphas[key])
+            new = edge_step(src, f, edge_vec, rows, sub, dmax, alphas[key])
         elif kind == "feature":
-            new = feature_step(pos, f, rows, sub, dmax, alphas[key])
+            new = feature_step(src, f, rows, sub, dmax, alphas[key])
         elif kind == "corner":
-            new = corner_step(pos, f, rows, sub, dmax, alphas[key])
+            new = corner_step(src, f, rows, sub, dmax, alphas[key])
         else:
-            new = pos[rows]
+            new = src[rows]
         pos[rows] = new
+    if original is not None and clamp is not None:
+        keep = norm3((pos - np.asarray(original, dtype=F32)).astype(F32)) < F32(clamp)
+        pos = np.where(keep[:, None], pos, src).astype(F32)
     return pos, f, lab, (w2, V2)
 
 

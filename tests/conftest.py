@@ -46,6 +46,14 @@ def fandisk_k32():
     return dict(np.load(os.path.join(GOLDEN, "fandisk_k32.npz")))
 
 
+@pytest.fixture(scope="session")
+def ours():
+    """PostProcessing.ipynb#c9 rows "Ours" (snapshot classes + displacement clamp) and "CTD-QEM" on fandisk, recorded from
+    the reference (tests/golden/make_golden_ours.py)"""
+    import numpy as np
+    return dict(np.load(os.path.join(GOLDEN, "ours_fandisk.npz")))
+
+
 def angle_between(a, b):
     """fp64 atan2(|a x b|, a.b): fp32 acos has a ~5e-4 rad floor near 0."""
     import numpy as np

@@ -370,9 +370,34 @@ def _fandisk_processor(ng, fandisk):
     return p
 
 
+def denoise_unfused(ng, p, k_feature: int = 16, k_update: int = 8, iterations: int = 2):
+    """Processor.denoise written against the public operators, call for call as the reference does it (Processor.py:119-139):
+    the cross-check of the fused session (test scaffolding; it lived in the product class in round 1)."""
+    g = p.graph
+    l = ng.TorchUtils.averageEdgeLength(g.pos, p.selector.getKNNSelection(6).getEdgeIndex())
+    d = float(2 * l)
+    alphas = [1, 0.2, 1]
+    for _ in range(iterations):
+        decomposition, f_n = p.getMyFeatureDecomposition(k_feature)
+        classes = decomposition.getClasses()
+        selection = p.selector.getKNNSelection(k_update)
+        for key in range(3):
+            indices = (classes == key).nonzero().flatten()
+            if indices.size(0) == 0:
+                continue
+            if key == 0:
+                new_pos = p.denoiser.flat_step(selection.filter(indices), f_n, d, alphas[key])
+            elif key == 1:
+                new_pos = p.denoiser.edge_step(selection.filter(indices), f_n, decomposition.eigvec[..., 0], d, alphas[key])
+            else:
+                new_pos = p.denoiser.feature_step(selection.filter(indices), f_n, d, alphas[key])
+            g.pos[indices] = new_pos
+        g.n = f_n
+
+
 def test_denoise_fused_equals_unfused(ng, fandisk):
     a = _fandisk_processor(ng, fandisk); a.denoise()
-    b = _fandisk_processor(ng, fandisk); b.denoise_unfused()
+    b = _fandisk_processor(ng, fandisk); denoise_unfused(ng, b)
     scale = float(a.graph.pos.abs().max())
     assert float((a.graph.pos - b.graph.pos).abs().max()) / scale < 2e-6
     assert angle_between(a.graph.n.cpu().numpy(), b.graph.n.cpu().numpy()).max() < 1e-4
@@ -383,7 +408,7 @@ def test_denoise_fused_equals_unfused_other_neighbourhoods(ng, fandisk, k_f, k_u
     """The fused session against the per-stage public operators for the neighbourhood sizes of BASELINE configs[2] (k = 32),
     the notebooks (64) and sizes without a specialised kernel (12 / 5): same labels' effect on positions, same normals."""
     a = _fandisk_processor(ng, fandisk); a._denoise_fused(k_f, k_u, 2)
-    b = _fandisk_processor(ng, fandisk); b.denoise_unfused(k_f, k_u, 2)
+    b = _fandisk_processor(ng, fandisk); denoise_unfused(ng, b, k_f, k_u, 2)
     scale = float(a.graph.pos.abs().max())
     assert float((a.graph.pos - b.graph.pos).abs().max()) / scale < 2e-6
     assert angle_between(a.graph.n.cpu().numpy(), b.graph.n.cpu().numpy()).max() < 1e-4
@@ -986,3 +1011,164 @@ def test_orientation_properties(ng):
     q.graph.n = cu(nrm).clone()
     q.graphBuilder.flipNormals()
     assert torch.equal(p.graph.n, q.graph.n)
+
+
+# ------------------------------------------------------------------------------------------------------
+# round 2: the notebook's "Ours" / "CTD-QEM" rows as fused session modes, digest, reservations, 10 M-point sampled check,
+# sampler / noise on the device
+# ------------------------------------------------------------------------------------------------------
+def _ours_session(ng, ours, t, strategy, alphas, dmax, clamp):
+    L = ng._lib
+    sess = L.Session(cu(ours["pos0"]), 16)
+    sess.set_state(cu(ours[t + "pos_in"]), cu(ours[t + "n_in"]))
+    if clamp:
+        sess.set_original(cu(ours["pos0"]))
+    params = L.make_params(16, 8, None, 0.3, 3.0, 0.2, strategy, alphas, dmax, L.STEP_SNAPSHOT_CLASSES, clamp)
+    sess.step(params)
+    return sess.get_state(True)
+
+
+@pytest.mark.parametrize("it", [0, 1])
+def test_ours_clamp_mode_vs_reference(ng, ours, it):
+    """PostProcessing.ipynb#c9 row "Ours" as ONE fused session step (NGPD_STEP_SNAPSHOT_CLASSES + clamp_radius), teacher-forced
+    on the reference's inputs of each iteration: labels, smoothed normals, clamped positions."""
+    L = ng._lib
+    t = f"ours{it}_"
+    d = float(ours["d"])
+    pos, fn, lab = _ours_session(ng, ours, t, (L.STEP_FLAT, L.STEP_FEATURE, L.STEP_FEATURE), (1.0, 0.2, 1.0), d * 20000, d)
+    lab, fn, pos = lab.cpu().numpy(), fn.cpu().numpy(), pos.cpu().numpy()
+    same = lab == ours[t + "classes"]
+    ang = angle_between(fn, ours[t + "f_n"])
+    err = np.abs(pos - ours[t + "pos_out"]).max(axis=1) / np.abs(ours["pos0"]).max()
+    print(f"\nOurs iteration {it}: labels differ {(~same).sum()}, normals > 1e-4 rad {(ang > 1e-4).mean():.4%}, positions > 1e-5 {(err > 1e-5).mean():.4%}")
+    # yardstick of one iteration (test_session_labels_vs_reference): the reference against itself under a 1-ulp change
+    assert (~same).sum() <= 7 and (ang > 1e-4).mean() < 0.0080 and (err > 1e-5).mean() < 0.0377
+    # rows whose stage-1 normals agree with the reference's in their whole update neighbourhood must agree to 1e-5
+    good = ang <= 1e-4
+    nbr = ng._lib.Grid(cu(ours["pos0"]), 8).knn(cu(ours[t + "pos_in"]), 8).cpu().numpy()
+    clean = good[nbr].all(axis=1) & same
+    assert clean.mean() > 0.95 and err[clean].max() < 1e-5, (clean.mean(), err[clean].max())
+
+
+def test_ctd_qem_mode_vs_reference(ng, ours):
+    """row "CTD-QEM": feature_step on every point from one snapshot = strategy feature/feature/feature in snapshot mode"""
+    L = ng._lib
+    pos, fn, _ = _ours_session(ng, ours, "qem0_", (L.STEP_FEATURE,) * 3, (1.0, 1.0, 1.0), float(ours["d"]), 0.0)
+    ang = angle_between(fn.cpu().numpy(), ours["qem0_f_n"])
+    err = np.abs(pos.cpu().numpy() - ours["qem0_pos_out"]).max(axis=1) / np.abs(ours["pos0"]).max()
+    assert (ang > 1e-4).mean() < 0.0080 and (err > 1e-5).mean() < 0.0377
+    nbr = L.Grid(cu(ours["pos0"]), 8).knn(cu(ours["qem0_pos_in"]), 8).cpu().numpy()
+    clean = (ang <= 1e-4)[nbr].all(axis=1)
+    assert err[clean].max() < 1e-5
+
+
+def test_snapshot_mode_equals_operator_composition(ng, ours):
+    """the fused "Ours" step against the same loop composed from the public operators (as the notebook writes it)"""
+    L = ng._lib
+    p = _processor(ng, ours["ours0_pos_in"], ours["ours0_n_in"], tree=ours["pos0"])
+    g = p.graph
+    d = float(ours["d"])
+    original = cu(ours["pos0"])
+    decomposition, f_n = p.getMyFeatureDecomposition()
+    classes = decomposition.getClasses()
+    selection = p.selector.getKNNSelection(8)
+    temp_pos = g.pos.clone()
+    for key in range(3):
+        indices = (classes == key).nonzero().flatten()
+        if indices.size(0) == 0:
+            continue
+        if key == 0:
+            new_pos = p.denoiser.flat_step(selection.filter(indices), f_n, d * 20000, [1, 0.2, 1][key])
+        else:
+            new_pos = p.denoiser.feature_step(selection.filter(indices), f_n, d * 20000, [1, 0.2, 1][key])
+        temp_pos[indices] = new_pos
+    mask = (temp_pos - original).norm(dim=1) < d
+    g.pos[mask] = temp_pos[mask]
+    pos, fn, lab = _ours_session(ng, ours, "ours0_", (L.STEP_FLAT, L.STEP_FEATURE, L.STEP_FEATURE), (1.0, 0.2, 1.0), d * 20000, d)
+    assert torch.equal(lab.long(), classes.long())
+    assert float((pos - g.pos).abs().max()) / float(original.abs().max()) < 2e-6
+    assert angle_between(fn.cpu().numpy(), f_n.cpu().numpy()).max() < 1e-4
+
+
+def test_checksum_is_order_independent_and_reserve_changes_nothing(ng):
+    L = ng._lib
+    n = 60000
+    pts = cu(surface_cloud(n, seed=3))
+    nrm = torch.nn.functional.normalize(torch.randn((n, 3), generator=torch.Generator().manual_seed(1)), dim=1).cuda()
+    a = L.Session(pts, 16)
+    a.set_state(pts, nrm)
+    s, c = a.mean_edge_length_parts(6)
+    params = L.make_params(dmax=2.0 * s / c)
+    for _ in range(2):
+        a.step(params)
+    da = a.checksum()
+    # the same cloud handed over in another order, with the permutation as global ids, and everything reserved up front
+    perm = torch.randperm(n, generator=torch.Generator().manual_seed(2)).cuda()
+    b = L.Session(pts[perm].contiguous(), 16)
+    b.reserve(16)
+    b.set_state(pts[perm].contiguous(), nrm[perm].contiguous())
+    for _ in range(2):
+        b.step(params)
+    db = b.checksum(perm)
+    assert da == db, (da, db)
+    assert da[10] == n and da[6] + da[7] + da[8] == n and da[9] == 0
+    pa, na, la = a.get_state(True)
+    assert da[6] == int((la == 0).sum()) and da[7] == int((la == 1).sum())
+    assert abs(da[2] - (1 << 64) * (da[2] >= (1 << 63)) - float(pa[:, 0].double().sum()) * 2 ** 24) < n
+    # a single changed bit changes the digest
+    pa2 = pa.clone(); pa2[17, 1] = torch.nextafter(pa2[17, 1], torch.tensor(9.0, device="cuda"))
+    a.set_state(pa2, na)
+    assert a.checksum()[0] != da[0]
+
+
+def test_step_at_10M_points_sampled_against_oracle(ng):
+    """A full-size step checked where the oracle can follow: sampled rows of a 10 M-point run against the exact search, an fp64
+    brute force and the NumPy oracle (bench.py's `validated` leg; VERDICT r1 weak #1)."""
+    import argparse
+    import bench
+    L = ng._lib
+    dev = torch.device("cuda", 0)
+    args = argparse.Namespace(surface="creased", strategy="flat/edge/feature", clamp=False)
+    n = 10_000_000
+    noisy, analytic, _ = bench.make_shard(args, n, dev, 0, 1)
+    nrm = bench.single_gpu_normals(noisy, analytic)
+    sess = L.Session(noisy, 16)
+    sess.set_state(noisy, nrm)
+    s, c = sess.mean_edge_length_parts(6)
+    params = L.make_params(dmax=2.0 * s / c)
+    for _ in range(3):
+        sess.step(params)                                       # iteration 3 answers most rows from stored candidates (tier 0)
+    v = bench.validate(args, sess, params, noisy, n, dev, 4000, 48)
+    print("\n10 M-point step:", v)
+    assert v["knn_rows_equal_exact_search"] == v["rows_sampled"] == 4000
+    assert v["knn_rows_equal_bruteforce"] == v["knn_rows_bruteforce_fp64"] == 48
+    assert v["labels_equal_oracle"] >= 3996
+    assert v["smoothed_normals_within_1e-4_rad_of_oracle"] >= 3960
+
+
+def test_sampler_and_noise_on_device(ng, tmp_path):
+    """Pointcloud.sampleObj / Noise.generateNoise with CUDA tensors (SURVEY 8f rank 3): samples lie on the mesh in proportion to
+    the face areas, are reproducible under the global seed, and the noise has the requested level along the normals."""
+    obj = tmp_path / "two_squares.obj"
+    obj.write_text("\n".join(["v 0 0 0", "v 1 0 0", "v 1 1 0", "v 0 1 0", "v 3 0 0", "v 3 2 0", "v 3 2 2", "v 3 0 2",
+                               "f 1 2 3", "f 1 3 4", "f 5 6 7", "f 5 7 8"]) + "\n")
+    torch.manual_seed(0); torch.cuda.manual_seed(0)
+    pc = ng.Pointcloud.sampleObj(str(obj), 2_000_000, device="cuda")
+    assert pc.v.is_cuda and pc.n.is_cuda and pc.v.shape == (2_000_000, 3)
+    v, nr = pc.v, pc.n
+    small, big = v[:, 2].abs() < 1e-6, (v[:, 0] - 3).abs() < 1e-6
+    assert bool((small | big).all())
+    assert abs(float(big.float().mean()) - 0.8) < 0.002
+    assert float((v[small, :2].mean(0) - 0.5).abs().max()) < 0.002 and float((v[big, 1:].mean(0) - 1.0).abs().max()) < 0.004
+    assert bool((nr[small].abs() - torch.tensor([0.0, 0.0, 1.0], device="cuda")).abs().max() < 1e-6)
+    torch.manual_seed(0); torch.cuda.manual_seed(0)
+    again = ng.Pointcloud.sampleObj(str(obj), 2_000_000, device="cuda")
+    assert torch.equal(again.v, pc.v)
+    # noise along the normal on a CUDA graph: sigma = level x mean edge length, positions move only along n
+    p = ng.Processor(ng.Pointcloud(pc.v.clone(), pc.n.clone()))
+    torch.manual_seed(5)
+    p.noise.generateNoise(0.3, 0.01, keepNormals=True)
+    off = p.graph.pos - p.graph.gt
+    along = (off * pc.n).sum(1)
+    assert float((off - along[:, None] * pc.n).abs().max()) < 1e-6
+    assert abs(float(along.std()) - 0.003) < 3e-5 and abs(float(along.mean())) < 2e-5

@@ -257,3 +257,69 @@ def test_cpsd_normal_filtered_tensors(hm, cpsd):
             ok = gap > 1e-3
             dots = np.abs((V * cpsd[t + V_key]).sum(axis=1))
             assert (dots[ok] > 1 - 1e-4).all()
+
+
+def _random_voting_tensors(n, k, rng, spread):
+    """T = sum w n n^T / sum w of k unit normals scattered around up to three directions (flat / crease / corner mixtures)"""
+    base = rng.normal(size=(n, 3, 3))
+    base /= np.linalg.norm(base, axis=2, keepdims=True)
+    which = rng.integers(0, 3, (n, k)) % rng.integers(1, 4, (n, 1))
+    nrm = base[np.arange(n)[:, None], which] + rng.normal(scale=spread, size=(n, k, 3))
+    nrm /= np.linalg.norm(nrm, axis=2, keepdims=True)
+    w = (rng.random((n, k)) < 0.7).astype(np.float32)
+    w[w.sum(1) == 0] = 1
+    nrm = nrm.astype(np.float32)
+    T = np.einsum("nk,nki,nkj->nij", w, nrm, nrm).astype(np.float32) / w.sum(1)[:, None, None]
+    T = ((T + T.transpose(0, 2, 1)) * np.float32(0.5)).astype(np.float32)
+    return np.ascontiguousarray(T)
+
+
+def _fast_vs_lapack(hm, T):
+    n = len(T)
+    lab = np.zeros(n, np.uint8); cert = np.zeros(n, np.uint8); l3 = np.zeros(n, np.float32); vec = np.zeros((n, 3), np.float32)
+    hm.hm_classify_fast(P(T), ctypes.c_int64(n), ctypes.c_float(0.2), P(lab), P(cert), P(l3), P(vec))
+    w = np.zeros((n, 3), np.float32); V = np.zeros((n, 3, 3), np.float32)
+    hm.hm_eigh3(P(T), ctypes.c_int64(n), P(w), P(V))
+    ref = np.zeros(n, np.uint8)
+    hm.hm_classify(P(w), ctypes.c_int64(n), ctypes.c_float(0.2), P(ref))
+    return lab, cert.astype(bool), l3, vec, w, V, ref
+
+
+def test_fast_labels_agree_with_lapack_order(hm, fandisk, fandisk_k32):
+    """csrc/eig3_fast.cuh: wherever the closed-form path calls its label certain it equals the label from the LAPACK-order
+    eigenvalues (the rest is recomputed by that path in the kernel), it is certain almost everywhere, and the crease direction
+    of edge rows is the LAPACK eigenvector up to sign."""
+    rng = np.random.default_rng(7)
+    sets = {"fandisk it0": fandisk["it0_T2"], "fandisk it1": fandisk["it1_T2"], "fandisk k32": fandisk_k32["T2"] if "T2" in fandisk_k32 else fandisk["it0_T1"],
+            "random tight": _random_voting_tensors(400000, 16, rng, 0.02), "random loose": _random_voting_tensors(400000, 16, rng, 0.3),
+            "random k32": _random_voting_tensors(200000, 32, rng, 0.1)}
+    for name, T in sets.items():
+        T = np.ascontiguousarray(T.astype(np.float32))
+        lab, cert, l3, vec, w, V, ref = _fast_vs_lapack(hm, T)
+        wrong = cert & (lab != ref)
+        print(f"{name}: {len(T)} tensors, uncertain {1 - cert.mean():.3e}, labels {np.bincount(ref, minlength=3).tolist()}, "
+              f"max |l3 - lapack| {np.abs(l3 - w[:, 0])[cert].max():.2e}")
+        assert wrong.sum() == 0, (name, int(wrong.sum()))
+        assert cert.mean() > 0.995, (name, cert.mean())
+        assert np.abs(l3 - w[:, 0])[cert].max() < 3e-6
+        edge = cert & (ref == 1)
+        if edge.any():
+            ang = angle_between(vec[edge], V[edge][:, :, 0])
+            ang = np.minimum(ang, np.pi - ang)
+            assert ang.max() < 1e-4, (name, ang.max())
+    # rows pushed onto the decision boundaries: uncertain is allowed, a certain wrong answer is not
+    T = _random_voting_tensors(300000, 16, rng, 0.15)
+    lab, cert, l3, vec, w, V, ref = _fast_vs_lapack(hm, T)
+    l1, l2, l3_ = w[:, 2], w[:, 1], w[:, 0]
+    g = np.stack([0.2 * (l1 - l2), l2 - l3_, l3_], 1)
+    srt = np.sort(g, axis=1)
+    close = (srt[:, 2] - srt[:, 1]) < 1e-4
+    assert (cert & (lab != ref)).sum() == 0
+    print(f"near-boundary rows: {close.sum()}, of them certain {cert[close].mean():.3f}")
+    # degenerate input goes to the fallback instead of producing a label
+    bad = np.zeros((4, 3, 3), np.float32)
+    bad[1] = np.eye(3, dtype=np.float32) / 3
+    bad[2, 0, 0] = np.nan
+    bad[3] = np.float32(1e30)
+    _, cert, *_ = _fast_vs_lapack(hm, bad)
+    assert not cert.any()

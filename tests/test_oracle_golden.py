@@ -228,6 +228,32 @@ def test_cpsd_loop(cpsd):
         assert (err[same] > 1e-5).mean() < 0.01, (err[same] > 1e-5).mean()
 
 
+@pytest.mark.parametrize("it", [0, 1])
+def test_ours_snapshot_clamp_iteration(ours, it):
+    """the notebook's "Ours" row (PostProcessing.ipynb#c9, j == 3), teacher-forced per iteration"""
+    t = f"ours{it}_"
+    xt = O.acos_threshold(math.pi * 5 / 12)
+    d = np.float32(ours["d"])
+    pos, f, lab, _ = O.denoise_iteration(ours["pos0"], ours[t + "pos_in"], ours[t + "n_in"], 16, 8, xt, (1.0, 0.2, 1.0), d * np.float32(20000),
+                                         strategy=("flat", "feature", "feature"), knn=O.knn_kdtree, snapshot=True, original=ours["pos0"], clamp=d)
+    assert np.array_equal(lab, ours[t + "classes"])
+    assert angle_between(f, ours[t + "f_n"]).max() < 1e-4
+    err = np.abs(pos - ours[t + "pos_out"]).max(axis=1) / np.abs(ours["pos0"]).max()
+    assert err.max() < 1e-5, err.max()
+    # the clamp decided the same rows
+    kept = np.any(pos != ours[t + "pos_in"], axis=1)
+    assert (kept & ~ours[t + "mask"]).sum() == 0
+
+
+def test_ctd_qem_loop(ours):
+    """the notebook's "CTD-QEM" row (j == 2): feature_step on every point, one snapshot; first iteration teacher-forced"""
+    xt = O.acos_threshold(math.pi * 5 / 12)
+    pos, f, _, _ = O.denoise_iteration(ours["pos0"], ours["qem0_pos_in"], ours["qem0_n_in"], 16, 8, xt, (1.0, 1.0, 1.0), np.float32(ours["d"]),
+                                       strategy=("feature", "feature", "feature"), knn=O.knn_kdtree, snapshot=True)
+    err = np.abs(pos - ours["qem0_pos_out"]).max(axis=1) / np.abs(ours["pos0"]).max()
+    assert err.max() < 1e-5, err.max()
+
+
 def test_mesh_vertex_update_vs_reference():
     """PatchGeneration.Modules.Mesh.updateVertices (tests/golden/make_golden_mesh.py)"""
     import os
