@@ -303,6 +303,53 @@ def validate(args, sess, params, tree_local, n_owned, device, sample_rows=10000,
     return out
 
 
+def run_extra(args, name, n, dev, surface, k_f, k_u, strategy, clamp, steps=6, warmup=4):
+    """A secondary configuration on one GPU (same generator, same timing rules), so that the driver's default run also shows
+    BASELINE configs[2] (k = 32 at 10 M points) and a surface that exercises edge_step / feature_step."""
+    import argparse
+    import torch
+    from ngpd_b200 import _lib
+    a = argparse.Namespace(**{**vars(args), "surface": surface, "strategy": strategy, "clamp": clamp})
+    noisy, analytic, _ = make_shard(a, n, dev, 0, 1)
+    nrm = single_gpu_normals(noisy, analytic)
+    del analytic
+    sess = _lib.Session(noisy, k_f)
+    sess.reserve(k_f)
+    sess.set_state(noisy, nrm)
+    s, c = sess.mean_edge_length_parts(6)
+    d = 2.0 * s / c
+    params = _lib.make_params(k_f, k_u, None, 0.3, 3.0, 0.2, strategy_of(a), ALPHAS, d * (20000.0 if clamp else 1.0),
+                              _lib.STEP_SNAPSHOT_CLASSES if clamp else 0, d if clamp else 0.0)
+    if clamp:
+        sess.set_original(noisy)
+    for _ in range(warmup):
+        sess.step(params)
+    sess.set_profiling(True)
+    sess.get_profile()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        sess.step(params)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    prof = sess.get_profile()
+    digest = sess.checksum()
+    tot = max(digest[6] + digest[7] + digest[8], 1)
+    peak, _ = measured_peak()
+    b_iter = 134 + 8 * k_f + 4 * k_u
+    out = {"name": name, "points": n, "surface": surface, "k_feature": k_f, "k_update": k_u, "strategy": strategy, "clamp_to_original": clamp,
+           "steps": steps, "warmup": warmup, "ms_per_step": ms, "value": n / (ms * 1e-3), "unit": "point-iterations/s",
+           "iteration_frac_of_hbm_peak": b_iter * n / (ms * 1e-3) / 1e9 / peak,
+           "class_histogram": {"flat": digest[6], "edge": digest[7], "corner": digest[8], "edge_fraction": digest[7] / tot,
+                               "corner_fraction": digest[8] / tot},
+           "kernels_ms_per_step": {k: v[0] / steps for k, v in prof.items() if v[1]}}
+    del sess, noisy, nrm
+    torch.cuda.empty_cache()
+    return out
+
+
 class _DevView:
     """zero-copy torch view of a raw device pointer"""
 
@@ -509,6 +556,17 @@ def run_ours(args):
                     "call": "ngpd_knn / ngpd_nn_sqdist (public ABI, queries = the tree's own noisy points, index output materialised)"}
         del tab, d2, grid
 
+    extra = None
+    if world == 1 and not args.no_extra:
+        del tree_local
+        torch.cuda.empty_cache()
+        m = min(n, 10_000_000)
+        extra = [run_extra(args, "BASELINE configs[2] stand-in: k = 32 / 8 at 10 M points", m, dev, "creased", 32, 8, "flat/edge/feature", False),
+                 run_extra(args, "dense creases: lattice of 17^3 cubes, Processor.denoise strategy", m, dev, "cubes", 16, 8, "flat/edge/feature", False),
+                 run_extra(args, "dense creases, the notebook's CTD-QEM row (feature_step on every point)", m, dev, "cubes", 16, 8,
+                           "feature/feature/feature", False),
+                 run_extra(args, "dense creases, the notebook's 'Ours' row (flat/feature/feature from one snapshot + displacement clamp)", m, dev,
+                           "cubes", 16, 8, "flat/feature/feature", True)]
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -550,7 +608,7 @@ def run_ours(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, n), "clocks": clocks,
             "e2e": e2e, "cold": cold, "validated": validated, "checksum": checksum, "class_histogram": class_histogram, "halo": halo,
-            "knn": knn_line, "gpu_launches": launches, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu}
+            "knn": knn_line, "extra_configs": extra, "gpu_launches": launches, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu}
     print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -569,6 +627,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-knn", action="store_true")
     ap.add_argument("--no-validate", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary single-GPU configurations (k = 32; dense-crease surface)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--k-feature", type=int, default=K_F, help="k of the feature pass (configs[2]: 32)")
     ap.add_argument("--k-update", type=int, default=K_U)

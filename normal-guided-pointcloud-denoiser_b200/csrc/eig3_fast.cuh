@@ -1,9 +1,10 @@
-// Labels and crease direction of the SECOND tensor pass without the LAPACK-order eigensolver.
+// Labels of the SECOND tensor pass without the LAPACK-order eigensolver.
 //
 // What stage 2 consumes (Decompositionor.py:57-69, Processor.py:134): the argmax of three ratios of the eigenvalues, and, for
-// the rows that edge_step will move, the eigenvector of the smallest eigenvalue up to sign (edge_step is even in y).  Neither
-// depends on LAPACK's eigenvector sign conventions -- unlike the smoothing of stage 1, which is why eig3.cuh exists -- so the
-// QL sweeps (~900 of the kernel's ~1 900 warp-instructions per 32 rows, profiles/r1m_instruction_mix.md) are replaced by:
+// the rows that edge_step will move, the eigenvector of the smallest eigenvalue.  The label does not depend on LAPACK's
+// eigenvector conventions -- unlike the smoothing of stage 1, which is why eig3.cuh exists -- so for every row that does not
+// need the vector the QL sweeps (~900 of the kernel's ~1 900 warp-instructions per 32 rows, profiles/r1m_instruction_mix.md)
+// are replaced by:
 //   * eigenvalues in closed form (trigonometric solution of the characteristic cubic of K = T - tr/3 I).  The closed form is
 //     unstable in fp32 (cancellation in p^3 - q^2 near a double root), so the invariants are accumulated in fp64 (about 25 fused
 //     multiply-adds); square roots and the angle functions act on well-conditioned quantities and stay fp32.
@@ -13,7 +14,8 @@
 //     leads by more than NGPD_FAST_LABEL_MARGIN; every other row (about 1 in 10^4, and all degenerate input) is handed to the
 //     LAPACK-order path by the caller, so the labels stay bit-identical to the reference's
 //     (tests/test_hostmath.py::test_fast_labels_agree_with_lapack_order, test_gpu_parity.py teacher-forced label tests).
-//   * the crease direction as the largest cross product of two rows of T - l3 I, only where it is used.
+// Rows moved by edge_step keep the LAPACK-order path: their 3x3 solve can be near-singular and amplifies a 1e-6 rad change of
+// the crease direction (measured with a cross-product eigenvector: one fandisk row off by 3e-4 of the extent).
 #pragma once
 #include "common.cuh"
 
@@ -24,7 +26,7 @@ namespace ngpd {
 struct FastLabel {
     int label;       // 0 flat, 1 edge, 2 corner
     bool certain;    // false: decide with eigh3_lapack + classify()
-    float l3;        // smallest eigenvalue (for the crease direction)
+    float l3;        // smallest eigenvalue
 };
 
 NGPD_HD FastLabel classify_fast(float xx, float xy, float xz, float yy, float yz, float zz, float scale) {
@@ -65,26 +67,6 @@ NGPD_HD FastLabel classify_fast(float xx, float xy, float xz, float yy, float yz
     o.l3 = l3;
     o.certain = (best - second) > NGPD_FAST_LABEL_MARGIN * fmaxf(l1, 1.0f);
     return o;
-}
-
-// unit eigenvector of the eigenvalue l (simple, as the smallest eigenvalue of an "edge" tensor is): the rows of T - l I span the
-// plane orthogonal to it, so it is parallel to every cross product of two rows; the longest one is the best conditioned
-NGPD_HD V3 eigvec_of(float xx, float xy, float xz, float yy, float yz, float zz, float l) {
-    const float a = xx - l, b = yy - l, c = zz - l;
-    // r0 = (a, xy, xz), r1 = (xy, b, yz), r2 = (xz, yz, c)
-    const V3 c01 = v3(fmaf(xy, yz, -xz * b), fmaf(xz, xy, -a * yz), fmaf(a, b, -xy * xy));
-    const V3 c02 = v3(fmaf(xy, c, -xz * yz), fmaf(xz, xz, -a * c), fmaf(a, yz, -xy * xz));
-    const V3 c12 = v3(fmaf(b, c, -yz * yz), fmaf(yz, xz, -xy * c), fmaf(xy, yz, -b * xz));
-    const float n01 = fmaf(c01.z, c01.z, fmaf(c01.y, c01.y, c01.x * c01.x));
-    const float n02 = fmaf(c02.z, c02.z, fmaf(c02.y, c02.y, c02.x * c02.x));
-    const float n12 = fmaf(c12.z, c12.z, fmaf(c12.y, c12.y, c12.x * c12.x));
-    V3 v = c01;
-    float nn = n01;
-    if (n02 > nn) { v = c02; nn = n02; }
-    if (n12 > nn) { v = c12; nn = n12; }
-    if (!(nn > 0.0f)) return v3(1.0f, 0.0f, 0.0f);
-    const float inv = 1.0f / sqrtf(nn);
-    return v3(v.x * inv, v.y * inv, v.z * inv);
 }
 
 }  // namespace ngpd

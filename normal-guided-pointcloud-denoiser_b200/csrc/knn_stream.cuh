@@ -283,6 +283,7 @@ __device__ __forceinline__ void ks_finalize(KsTop<KT>& t, const float4* __restri
 struct KsRowGlobal {
     const int32_t* __restrict__ row;
     __device__ __forceinline__ int operator()(int a) const { return __ldg(row + a); }
+    __device__ __forceinline__ int4 chunk(int c) const { return __ldg(reinterpret_cast<const int4*>(row) + c); }
 };
 
 // Candidate rows of the 128 consecutive queries of a block, staged through shared memory: the block's rows are one
@@ -312,6 +313,26 @@ struct KsRowShared {
     const KsCandTile<KT>& tile;
     int col;
     __device__ __forceinline__ int operator()(int a) const { return tile.v[a][col]; }
+    __device__ __forceinline__ int4 chunk(int c) const {
+        return make_int4(tile.v[4 * c][col], tile.v[4 * c + 1][col], tile.v[4 * c + 2][col], tile.v[4 * c + 3][col]);
+    }
+};
+
+// The same rows staged by the TMA unit (cp.async.bulk, completion on an mbarrier): every query's candidate row is one contiguous,
+// 16-byte-aligned piece of the candidate array, copied by ONE bulk-copy instruction of its own thread into a row of shared
+// memory -- no register round trip, no per-element shared-memory stores, no block barrier after the fill.  Rows are padded to an
+// odd number of 16-byte units, so the 16-byte vector reads of a lane's own row are free of bank conflicts (8 lanes x 16 bytes
+// cover the 32 banks), and the sorted row leaves the same way: written into the lane's row, stored to the neighbour table by
+// one bulk copy per thread (cp.async.bulk.global.shared::cta).
+template <int KT>
+struct KsCandRows {
+    static constexpr int STRIDE = KT + 4;                        // ints: KT / 4 + 1 units of 16 bytes, odd for KT = 16, 32, 64
+    alignas(128) int v[128][STRIDE];
+};
+struct KsRowPadded {
+    const int* row;
+    __device__ __forceinline__ int operator()(int a) const { return row[a]; }
+    __device__ __forceinline__ int4 chunk(int c) const { return *reinterpret_cast<const int4*>(row + 4 * c); }
 };
 
 // Keys of the re-ranking tier: a candidate is one of at most 64 slots of the row, so only 6 id bits are needed and the
@@ -326,13 +347,18 @@ template <int K, class Ids>
 __device__ __forceinline__ void ks_rerank_keys(const Ids& ids, int first, const float4* __restrict__ pts,
                                                float qx, float qy, float qz, float inv_h2, unsigned (&out)[K]) {
 #pragma unroll
-    for (int a = 0; a < K; ++a) {
-        const int j = ids(first + a);
-        const float4 p = __ldg(pts + max(j, 0));
-        const float dx = p.x - qx, dy = p.y - qy, dz = p.z - qz;
-        const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-        const float y = fminf(fmaf(d2, inv_h2, 32.0f), 63.99999f);      // NaN and far-away candidates saturate
-        out[a] = j >= 0 ? ((__float_as_uint(y) << KS_RR_SHIFT) | (unsigned)(first + a)) : KS_NONE;
+    for (int c = 0; c < K / 4; ++c) {
+        const int4 q4 = ids.chunk(first / 4 + c);                        // 16 bytes of ids per access
+        const int jj[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int a = 4 * c + e, j = jj[e];
+            const float4 p = __ldg(pts + max(j, 0));
+            const float dx = p.x - qx, dy = p.y - qy, dz = p.z - qz;
+            const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            const float y = fminf(fmaf(d2, inv_h2, 32.0f), 63.99999f);  // NaN and far-away candidates saturate
+            out[a] = j >= 0 ? ((__float_as_uint(y) << KS_RR_SHIFT) | (unsigned)(first + a)) : KS_NONE;
+        }
     }
 }
 

@@ -9,8 +9,10 @@
 // `owned` (optional) marks the rows this rank computes; the remaining rows are halo copies of points owned by
 // another GPU, refreshed between phases by ngpd_session_{export,import}_rows.
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 #include <algorithm>
+#include <cuda/ptx>
 #include "knn_stream.cuh"
 #include "point_math.cuh"
 #include "../../include/ngpd.h"
@@ -133,7 +135,7 @@ __device__ __forceinline__ void note_halo_need(float* __restrict__ need, bool ac
     if (active) {
         const float4 t = __ldg(tree_pts + s);
         const float dx = q.x - t.x, dy = q.y - t.y, dz = q.z - t.z;
-        v = (float)sqrt(dk2) * 1.000001f + sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx))) * 1.000001f;
+        v = sqrtf((float)dk2) * 1.000001f + sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx))) * 1.000001f;   // (rounded up: a bound, not a value)
         if (!(v == v)) v = 3.0e38f;
     }
     const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(v));
@@ -185,7 +187,7 @@ __device__ __forceinline__ void session_write_row(int64_t s, int k, const int (&
 // (Measured and dropped: staging the window of 512-768 tree points around the block's rows in shared memory and gathering
 // the candidates' coordinates from there when they fall inside it -- 1.00 -> 1.17 ms at 10 M points, k = 16: the extra
 // select per candidate costs more than the L1 look-ups it saves.  6 instead of 5 blocks per SM (80 registers): no change.)
-template <int K>
+template <int K, bool LEGACY_STORE>
 __global__ void __launch_bounds__(128, K <= 16 ? 5 : 4) session_knn_rerank_kernel(GridView g, const float4* __restrict__ pos, const uint8_t* __restrict__ owned,
                                                                  int64_t n, int k, int32_t* __restrict__ idx, KnnTrack tr,
                                                                  int32_t* __restrict__ fail_list, int32_t* __restrict__ fail_count) {
@@ -200,30 +202,126 @@ __global__ void __launch_bounds__(128, K <= 16 ? 5 : 4) session_knn_rerank_kerne
     constexpr int KF = ks_kf(K, 2 * K);
     KsTop<KF> top;
     double ex[KF];
-    // (rows that are not this rank's, or past the end, re-rank whatever their column holds -- zeros unless searched before -- and drop the result)
-    bool ok = ks_rerank<K>(top, g, KsRowShared<2 * K>{tile, (int)threadIdx.x}, an, q.x, q.y, q.z, ex);
+    // (lanes whose row is not this rank's, or past the end, re-rank whatever their column holds -- zeros unless searched before --
+    // and drop the result; a warp without any row of its own -- halo rows come in runs of tree order -- skips the work)
+    bool ok = false;
+    if (__any_sync(FULL, active)) ok = ks_rerank<K>(top, g, KsRowShared<2 * K>{tile, (int)threadIdx.x}, an, q.x, q.y, q.z, ex);
+    else {
+#pragma unroll
+        for (int a = 0; a < KF; ++a) { top.id[a] = 0; ex[a] = 0.0; }
+    }
     ok = ok && active && an.w > 0.0f;
     if (tr.need) note_halo_need(tr.need, ok, ex[K - 1], q, g.pts, s);
+    bool bulk_pending = false;
     if (k == K) {
-        // rows out through the tile as well: the block's 128 rows are one contiguous 128*K*4-byte piece of the table, written
-        // with coalesced 16-byte stores (a lane storing its own 64-byte row touches a cache line per two lanes)
-        __shared__ uint8_t row_ok[128];
-        __syncthreads();                                   // every lane is done reading candidate ids
+        if constexpr (K <= 16 && !LEGACY_STORE) {
+            // Rows out by TMA: a warp's 32 rows are one contiguous 32*K*4-byte piece of the neighbour table.  Every lane puts its
+            // row into a row-major staging area (16-byte stores), one elected lane hands the piece to the bulk-copy engine
+            // (cp.async.bulk.global.shared::cta) -- no block barrier, no transposed read-back, no per-lane global stores.
+            // Rows that failed the certificate are written too: they are on the hand-over list and every one of them is
+            // rewritten by a search tier later in the stream before anything reads the table.
+            namespace ptx = cuda::ptx;
+            __shared__ alignas(128) int rows_out[128 * K];
+            int4* mine = reinterpret_cast<int4*>(rows_out + threadIdx.x * K);
 #pragma unroll
-        for (int a = 0; a < K; ++a) tile.v[a][threadIdx.x] = top.id[a];
-        row_ok[threadIdx.x] = ok;
-        __syncthreads();
-        constexpr int CH = K / 4;
-        int4* dst = reinterpret_cast<int4*>(idx + row0 * K);
+            for (int c = 0; c < K / 4; ++c) mine[c] = make_int4(top.id[4 * c], top.id[4 * c + 1], top.id[4 * c + 2], top.id[4 * c + 3]);
+            ptx::fence_proxy_async(ptx::space_shared);               // generic-proxy stores -> visible to the async proxy
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) {
+                const int64_t w0 = row0 + (threadIdx.x & ~31);
+                const int64_t rows = n - w0 < 32 ? n - w0 : 32;
+                if (rows > 0) {
+                    ptx::cp_async_bulk(ptx::space_global, ptx::space_shared, idx + w0 * K, rows_out + (threadIdx.x & ~31) * K,
+                                       (uint32_t)(rows * K * sizeof(int32_t)));
+                    ptx::cp_async_bulk_commit_group();
+                    bulk_pending = true;
+                }
+            }
+        } else {
+            // rows out through the tile as well: the block's 128 rows are one contiguous 128*K*4-byte piece of the table, written
+            // with coalesced 16-byte stores (a lane storing its own 64-byte row touches a cache line per two lanes)
+            __shared__ uint8_t row_ok[128];
+            __syncthreads();                                   // every lane is done reading candidate ids
 #pragma unroll
-        for (int i = 0; i < CH; ++i) {
-            const int c = (int)threadIdx.x + 128 * i, r = c / CH, a0 = (c % CH) * 4;
-            if (row_ok[r]) dst[c] = make_int4(tile.v[a0][r], tile.v[a0 + 1][r], tile.v[a0 + 2][r], tile.v[a0 + 3][r]);
+            for (int a = 0; a < K; ++a) tile.v[a][threadIdx.x] = top.id[a];
+            row_ok[threadIdx.x] = ok;
+            __syncthreads();
+            constexpr int CH = K / 4;
+            int4* dst = reinterpret_cast<int4*>(idx + row0 * K);
+#pragma unroll
+            for (int i = 0; i < CH; ++i) {
+                const int c = (int)threadIdx.x + 128 * i, r = c / CH, a0 = (c % CH) * 4;
+                if (row_ok[r]) dst[c] = make_int4(tile.v[a0][r], tile.v[a0 + 1][r], tile.v[a0 + 2][r], tile.v[a0 + 3][r]);
+            }
         }
     } else if (ok) {
         session_write_row<K, KF>(s, k, top.id, idx);
     }
     fix_append(active && !ok, (int)s, fail_list, fail_count);
+    if (bulk_pending) cuda::ptx::cp_async_bulk_wait_group_read(cuda::ptx::n32_t<0>{});   // shared memory must outlive the copy that reads it
+}
+
+// tier 0 with the candidate rows staged by TMA (north star kernel 2: "stages candidates in shared memory via TMA"): see KsCandRows.
+// The arithmetic is ks_rerank, as in the kernel above, so the rows are bit-identical; what changes is the data movement:
+//   fill   one cp.async.bulk (global -> shared, mbarrier complete_tx) per thread for its own 8 K-byte row instead of coalesced
+//          16-byte loads into registers + 2 K scalar shared-memory stores per thread + a block barrier;
+//   reads  K / 2 16-byte shared loads per lane instead of 2 K scalar ones;
+//   store  the sorted row goes back through the lane's own shared row and one cp.async.bulk (shared -> global) per thread
+//          instead of K shared stores, two block barriers and a transposed read-back.
+// Every thread touches only its own row of the tile: the only block-wide synchronisation left is the mbarrier itself.
+template <int K>
+__global__ void __launch_bounds__(128, K <= 16 ? 5 : 4) session_knn_rerank_tma_kernel(GridView g, const float4* __restrict__ pos, const uint8_t* __restrict__ owned,
+                                                                     int64_t n, int k, int32_t* __restrict__ idx, KnnTrack tr,
+                                                                     int32_t* __restrict__ fail_list, int32_t* __restrict__ fail_count) {
+    namespace ptx = cuda::ptx;
+    constexpr int KT = 2 * K;
+    __shared__ KsCandRows<KT> tile;
+    __shared__ alignas(8) uint64_t bar;
+    const int tid = threadIdx.x;
+    const int64_t s0 = (int64_t)blockIdx.x * blockDim.x + tid;
+    if (tid == 0) {
+        ptx::mbarrier_init(&bar, 128);
+        ptx::fence_mbarrier_init(ptx::sem_release, ptx::scope_cluster);
+    }
+    __syncthreads();
+    int* myrow = tile.v[tid];
+    if (s0 < n) {
+        ptx::mbarrier_arrive_expect_tx(ptx::sem_release, ptx::scope_cta, ptx::space_shared, &bar, (uint32_t)(KT * sizeof(int32_t)));
+        ptx::cp_async_bulk(ptx::space_cluster, ptx::space_global, myrow, tr.cand + s0 * KT, (uint32_t)(KT * sizeof(int32_t)), &bar);
+    } else {
+        // past the end (last block): an all-zero row, valid ids whose result is dropped
+#pragma unroll
+        for (int c = 0; c < KT / 4; ++c) reinterpret_cast<int4*>(myrow)[c] = make_int4(0, 0, 0, 0);
+        ptx::mbarrier_arrive(&bar);
+    }
+    const bool active = s0 < n && (!owned || owned[s0]);
+    const int64_t s = active ? s0 : 0;
+    const float4 q = __ldg(pos + s), an = __ldg(tr.anchor + s);     // in flight while the rows arrive
+    while (!ptx::mbarrier_try_wait_parity(&bar, 0)) {}
+    constexpr int KF = ks_kf(K, 2 * K);
+    KsTop<KF> top;
+    double ex[KF];
+    bool ok = false;
+    if (__any_sync(FULL, active)) ok = ks_rerank<K>(top, g, KsRowPadded{myrow}, an, q.x, q.y, q.z, ex);
+    else {
+#pragma unroll
+        for (int a = 0; a < KF; ++a) { top.id[a] = 0; ex[a] = 0.0; }
+    }
+    ok = ok && active && an.w > 0.0f;
+    if (tr.need) note_halo_need(tr.need, ok, ex[K - 1], q, g.pts, s);
+    if (k == K) {
+        // (the lane is done reading its candidate ids: top.id[] holds what it needs)
+#pragma unroll
+        for (int c = 0; c < K / 4; ++c)
+            reinterpret_cast<int4*>(myrow)[c] = make_int4(top.id[4 * c], top.id[4 * c + 1], top.id[4 * c + 2], top.id[4 * c + 3]);
+        ptx::fence_proxy_async(ptx::space_shared);                  // the bulk copy reads shared memory through the async proxy
+        if (ok) ptx::cp_async_bulk(ptx::space_global, ptx::space_shared, idx + s * K, myrow, (uint32_t)(K * sizeof(int32_t)));
+        ptx::cp_async_bulk_commit_group();
+    } else if (ok) {
+        session_write_row<K, KF>(s, k, top.id, idx);
+    }
+    fix_append(active && !ok, (int)s, fail_list, fail_count);
+    if (k == K) ptx::cp_async_bulk_wait_group_read(ptx::n32_t<0>{});   // shared memory must outlive the copies that read it
 }
 
 // tiers 1 (R = 1) and 2 (R = 2) of the streaming search.  KT == K: plain search.  KT == 2K: the search also stores
@@ -380,9 +478,9 @@ __global__ void __launch_bounds__(128) session_nvt_smooth_late_kernel(Quad4 pos,
 // stage 2: filtered NVT on the smoothed normals, label + crease direction out.  With part != nullptr the kernel also
 // leaves, per block, {sum x, sum y, sum z, count} over the first ku neighbours of the rows it labelled sum_key
 // (flat_step's centre, Denoiser.py:106): the positions were just gathered, so the separate pass over the class is saved.
-// FAST: labels from closed-form eigenvalues, crease direction by cross products (eig3_fast.cuh); rows whose label is not certain
-// that way, and every row when FAST is off (a strategy applies edge_step to class 0 or 2, whose smallest eigenvalue is not
-// simple), go through the LAPACK-order solver.  edge_mask: bit l set = rows labelled l need their crease direction stored.
+// FAST: labels from closed-form eigenvalues (eig3_fast.cuh); rows whose label is not certain that way, rows that need their crease
+// direction (edge_mask: bit l set = rows labelled l are moved by edge_step), and every row when FAST is off go through the
+// LAPACK-order solver.
 template <int K, bool FAST>
 __global__ void __launch_bounds__(128, K == 16 ? 9 : (K == 32 ? 6 : 1)) session_nvt_classify_kernel(Quad4 pos, Quad4 fn, const uint8_t* __restrict__ owned,
                                                                    const int32_t* __restrict__ idx, int64_t n, int k, float x_thresh,
@@ -408,10 +506,12 @@ __global__ void __launch_bounds__(128, K == 16 ? 9 : (K == 32 ? 6 : 1)) session_
         V3 y = v3(0.0f, 0.0f, 0.0f);
         bool full = !FAST;
         if (FAST) {
+            // rows that edge_step will move keep the LAPACK-order eigenvector: its solve can be near-singular and
+            // then amplifies even a 1e-6 rad change of y -- measured: one fandisk row moved by 3e-4 of the extent with a
+            // cross-product eigenvector, so the fused step would no longer equal the operator-by-operator one
             const FastLabel f = classify_fast(t6[0], t6[1], t6[2], t6[3], t6[4], t6[5], scale);
             lab = f.label;
-            full = !f.certain;
-            if (!full && ((edge_mask >> lab) & 1)) y = eigvec_of(t6[0], t6[1], t6[2], t6[3], t6[4], t6[5], f.l3);
+            full = !f.certain || ((edge_mask >> lab) & 1);
         }
         if (full) {
             const LabelVec o = classify_lapack(t6[0], t6[1], t6[2], t6[3], t6[4], t6[5], scale);
@@ -915,8 +1015,20 @@ static int run_knn_fast(ngpd_session* S, int k, int32_t* idx, cudaStream_t st, b
     if constexpr (CAN_TRACK) {
         if (rerank_ok && S->cand_k == K) {
             // tier 0 first; what it cannot answer is searched (tracked: re-anchored, untracked: just answered)
-            session_knn_rerank_kernel<K><<<(unsigned)cdiv(S->n, 128), 128, 0, st>>>(g, S->pos[S->cur], S->owned, S->n, k, idx, KnnTrack{S->cand, S->anchor, S->owned ? S->halo_need : nullptr},
-                                                                                L.list[0], L.cnt[0]);
+            // A/B measurements (profiles/): NGPD_RERANK=ldg  round 1's kernel (coalesced loads, transposed tile, rows stored through the tile);
+            //                               NGPD_RERANK=rows candidate rows AND result rows by one bulk copy per thread (measured: 15 % slower --
+            //                                               128 small bulk copies per block cost the TMA unit more than the stores they replace);
+            //                               default        coalesced loads + transposed tile for the candidates, result rows by one bulk copy per warp
+            static const char* mode_env = getenv("NGPD_RERANK");
+            static const int mode = !mode_env ? 0 : (!strcmp(mode_env, "ldg") ? 1 : (!strcmp(mode_env, "rows") ? 2 : 0));
+            const KnnTrack trk{S->cand, S->anchor, S->owned ? S->halo_need : nullptr};
+            const unsigned rb = (unsigned)cdiv(S->n, 128);
+            if (mode == 1)
+                session_knn_rerank_kernel<K, true><<<rb, 128, 0, st>>>(g, S->pos[S->cur], S->owned, S->n, k, idx, trk, L.list[0], L.cnt[0]);
+            else if (mode == 2)
+                session_knn_rerank_tma_kernel<K><<<rb, 128, 0, st>>>(g, S->pos[S->cur], S->owned, S->n, k, idx, trk, L.list[0], L.cnt[0]);
+            else
+                session_knn_rerank_kernel<K, false><<<rb, 128, 0, st>>>(g, S->pos[S->cur], S->owned, S->n, k, idx, trk, L.list[0], L.cnt[0]);
             if (track) run_knn_tiers<K, 2 * K>(S, k, idx, st, true);
             else run_knn_tiers<K, K>(S, k, idx, st, true);
             S->knn_launches = 4;
@@ -1161,12 +1273,12 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_phase_feature
         int32_t* cls = S->cls;
         NGPD_CUDA_OK(cudaMemsetAsync(cls + 2 * S->n, 0, 2 * sizeof(int32_t), st));
         S->lists_ready = true;
-        // which labels' rows need their crease direction (edge_step's y, Processor.py:134); the closed-form stage-2 path serves
-        // the default strategies, a strategy with edge_step on class 0 or 2 keeps the LAPACK-order vectors for every row
+        // which labels' rows need their crease direction (edge_step's y, Processor.py:134): those rows keep the LAPACK-order solver,
+        // all others get their label from the closed form; with edge_step on class 0 (the majority) there is nothing to gain
         int edge_mask = 0;
         for (int key = 0; key < 3; ++key) if (p->strategy[key] == NGPD_STEP_EDGE) edge_mask |= 1 << key;
         static const bool fast_off = getenv("NGPD_NO_FAST_LABELS") != nullptr;   // measurements / A-B tests only
-        const bool fast = !fast_off && (edge_mask & ~2) == 0;
+        const bool fast = !fast_off && (edge_mask & 1) == 0;
         { ProfScope ps(S, st, 2);
           Quad4 fq{S->fn};
 #define NGPD_CLASSIFY(KK, FF) session_nvt_classify_kernel<KK, FF><<<b, 128, 0, st>>>(pos, fq, S->owned, S->idx, S->n, kf, p->x_thresh, p->scale, S->label, S->edge, edge_mask, 0, p->k_update, part, S->sum_scale, cls)

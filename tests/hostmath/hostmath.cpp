@@ -73,14 +73,12 @@ void hm_classify(const float* w, int64_t m, float scale, uint8_t* lab) {
     for (int64_t r = 0; r < m; ++r) lab[r] = (uint8_t)classify(w + 3 * r, scale);
 }
 
-// stage-2 shortcut (csrc/eig3_fast.cuh): label, certainty flag, smallest eigenvalue, crease direction per tensor
-void hm_classify_fast(const float* T, int64_t m, float scale, uint8_t* lab, uint8_t* certain, float* l3, float* vec) {
+// stage-2 shortcut (csrc/eig3_fast.cuh): label, certainty flag, smallest eigenvalue per tensor
+void hm_classify_fast(const float* T, int64_t m, float scale, uint8_t* lab, uint8_t* certain, float* l3) {
     for (int64_t r = 0; r < m; ++r) {
         const float* a = T + 9 * r;
         FastLabel f = classify_fast(a[0], a[3], a[6], a[4], a[7], a[8], scale);
         lab[r] = (uint8_t)f.label; certain[r] = f.certain; l3[r] = f.l3;
-        V3 v = eigvec_of(a[0], a[3], a[6], a[4], a[7], a[8], f.l3);
-        vec[3 * r] = v.x; vec[3 * r + 1] = v.y; vec[3 * r + 2] = v.z;
     }
 }
 
