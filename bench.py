@@ -440,6 +440,9 @@ def run_ours(args):
     launches = profile_src.launch_count() * args.steps
     clocks = sampler.stop() if sampler else None
     value = n * args.steps / (ms * 1e-3)
+    t0, t1, t2 = sess.knn_stats()                               # rows of the last search that each tier handed on (rank 0's slab)
+    knn_tiers = {"rows": n_local, "reranked_from_stored_candidates": n_local - t0, "searched_3x3x3": t0 - t1, "searched_5x5x5": t1 - t2,
+                 "exact_shell_search": t2}
 
     # ---- what the run computed: digest of the final state (compare across --gpus), labels of the last iteration, halo margin
     if world == 1:
@@ -608,7 +611,7 @@ def run_ours(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, n), "clocks": clocks,
             "e2e": e2e, "cold": cold, "validated": validated, "checksum": checksum, "class_histogram": class_histogram, "halo": halo,
-            "knn": knn_line, "extra_configs": extra, "gpu_launches": launches, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu}
+            "knn": knn_line, "knn_tiers_last_step": knn_tiers, "extra_configs": extra, "gpu_launches": launches, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu}
     print(json.dumps(line))
     if world > 1:
         dist.barrier()

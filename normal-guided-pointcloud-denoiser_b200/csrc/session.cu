@@ -691,8 +691,8 @@ __device__ __forceinline__ V3 clamp_to_original(V3 moved, V3 old, const float4* 
 }
 
 // one class: members move, everybody else is copied through to the other buffer (snapshot semantics)
-template <int KU>
-__global__ void __launch_bounds__(128, 10) session_update_kernel(int kind, int key, Quad4 pos, Quad4 fn, const float4* __restrict__ edge,
+template <int KU, int MINB>
+__global__ void __launch_bounds__(128, MINB) session_update_kernel(int kind, int key, Quad4 pos, Quad4 fn, const float4* __restrict__ edge,
                                                              const uint8_t* __restrict__ label, const uint8_t* __restrict__ owned,
                                                              const int32_t* __restrict__ idx, int64_t n, int k, int ku, float alpha, float dmax,
                                                              const float* __restrict__ cd, const float4* __restrict__ orig, float clamp_r,
@@ -1210,8 +1210,13 @@ static int features_knn(ngpd_session_t* S, const ngpd_step_params_t* p, cudaStre
     if (rc) return rc;
     S->idx_k = kf;
     if ((rc = ensure_tail(S, st))) return rc;
-    static const bool tail_off = getenv("NGPD_NO_TAIL_OVERLAP") != nullptr;   // measurements only
-    S->overlap_tail = !tail_off;   // honoured by the tiered search only (5 <= k <= 32, not in exact-only mode)
+    // Round 1 ran the last two search tiers on a high-priority side stream under the first tensor pass (-0.09 ms per iteration at
+    // 10 M points then).  Measured again in round 2 with the wider 5x5x5 tier (36 KB of shared memory per block): equal at 10 M
+    // points, but at 100 M points the iteration is 3 ms SLOWER with the overlap (28.1 vs 25.1 ms; ncu: the kernels themselves
+    // add up to the shorter figure) -- the search blocks' shared memory is carved out of the L1 that the gather-bound tensor
+    // pass lives on (L1 hit 80 %), for as long as the two kernels share the SMs.  Off by default; NGPD_TAIL_OVERLAP=1 turns it on.
+    static const bool tail_on = getenv("NGPD_TAIL_OVERLAP") != nullptr;
+    S->overlap_tail = tail_on;     // honoured by the tiered search only (5 <= k <= 32, not in exact-only mode)
     { ProfScope ps(S, st, 0); rc = run_knn(S, kf, S->idx, st, true); }
     S->overlap_tail = false;
     if (rc) return rc;
@@ -1360,14 +1365,15 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_phase_update(
         S->sums_ready = false;
         return 0;
     }
-    if (fixed8)
-        session_update_kernel<8><<<(unsigned)cdiv(S->n, 128), 128, 0, st>>>(kind, key, Quad4{S->pos[S->cur]}, Quad4{S->fn}, S->edge, S->label, S->owned,
-                                                                            S->idx, S->n, S->idx_k, p->k_update, p->alpha[key], p->dmax, S->cd,
-                                                                            orig, p->clamp_radius, S->pos[S->cur ^ 1]);
-    else
-        session_update_kernel<0><<<(unsigned)cdiv(S->n, 128), 128, 0, st>>>(kind, key, Quad4{S->pos[S->cur]}, Quad4{S->fn}, S->edge, S->label, S->owned,
-                                                                            S->idx, S->n, S->idx_k, p->k_update, p->alpha[key], p->dmax, S->cd,
-                                                                            orig, p->clamp_radius, S->pos[S->cur ^ 1]);
+    // registers per thread: 10 blocks per SM (48 registers) keep more warps, 6 blocks (80 registers) let all 16 neighbour gathers of a
+    // row be in flight at once; NGPD_UPDATE_BLOCKS selects for A/B measurements (profiles/)
+    static const char* ub_env = getenv("NGPD_UPDATE_BLOCKS");
+    static const int ub = ub_env ? atoi(ub_env) : 10;
+#define NGPD_UPDATE(KU_, MB_) session_update_kernel<KU_, MB_><<<(unsigned)cdiv(S->n, 128), 128, 0, st>>>(kind, key, Quad4{S->pos[S->cur]}, Quad4{S->fn}, S->edge, S->label, S->owned, \
+                                                                            S->idx, S->n, S->idx_k, p->k_update, p->alpha[key], p->dmax, S->cd, orig, p->clamp_radius, S->pos[S->cur ^ 1])
+    if (fixed8) { if (ub == 6) NGPD_UPDATE(8, 6); else if (ub == 8) NGPD_UPDATE(8, 8); else NGPD_UPDATE(8, 10); }
+    else NGPD_UPDATE(0, 10);
+#undef NGPD_UPDATE
     NGPD_CUDA_OK(cudaGetLastError());
     S->cur ^= 1;
     S->sums_ready = false;
@@ -1417,12 +1423,13 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_mean_edge_len
     cudaStream_t st = (cudaStream_t)stream_;
     NGPD_REQUIRE(S && out_host && k >= 1 && k <= 64, "ngpd_session_mean_edge_length: bad argument");
     { int rc = slab_flush(S, st); if (rc) return rc; }
-    int32_t* idx = nullptr;
-    double *acc = nullptr, *part = nullptr;
+    // stream-ordered scratch (pool-backed after the first call; returned on every exit path)
+    StreamBuf<int32_t> idx(st);
+    StreamBuf<double> acc(st), part(st);
     const unsigned blocks = strided(S->n, 256);
-    NGPD_CUDA_OK(cudaMallocAsync(&idx, (size_t)S->n * k * sizeof(int32_t), st));
-    NGPD_CUDA_OK(cudaMallocAsync(&acc, 4 * sizeof(double), st));
-    NGPD_CUDA_OK(cudaMallocAsync(&part, (size_t)blocks * 4 * sizeof(double), st));
+    NGPD_CUDA_OK(idx.alloc((size_t)S->n * k));
+    NGPD_CUDA_OK(acc.alloc(4));
+    NGPD_CUDA_OK(part.alloc((size_t)blocks * 4));
     int rc = run_knn(S, k, idx, st);
     if (rc) return rc;
     session_edge_len_kernel<<<blocks, 256, 0, st>>>(Quad4{S->pos[S->cur]}, S->owned, idx, S->n, k, part);
@@ -1430,9 +1437,6 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_mean_edge_len
     double h[2];
     NGPD_CUDA_OK(cudaMemcpyAsync(h, acc, sizeof(h), cudaMemcpyDeviceToHost, st));
     NGPD_CUDA_OK(cudaStreamSynchronize(st));
-    NGPD_CUDA_OK(cudaFreeAsync(idx, st));
-    NGPD_CUDA_OK(cudaFreeAsync(acc, st));
-    NGPD_CUDA_OK(cudaFreeAsync(part, st));
     out_host[0] = h[0]; out_host[1] = h[1];   // {sum of edge lengths, edge count}: callers divide (and all-reduce first on multi-GPU)
     return 0;
 }

@@ -317,8 +317,10 @@ def halo_width_from_box(lo: torch.Tensor, hi: torch.Tensor, n: int, k: int, fact
 
 def estimate_halo_width_sharded(tree_pos: torch.Tensor, k: int, group=None, factor: float = 6.0) -> float:
     """estimate_halo_width when every rank holds only a shard of the cloud"""
-    lo, hi = tree_pos.min(dim=0).values, tree_pos.max(dim=0).values
-    cnt = torch.tensor([tree_pos.size(0)], dtype=torch.long, device=tree_pos.device)
+    dev = tree_pos.device
+    lo = tree_pos.min(dim=0).values if tree_pos.numel() else torch.full((3,), float("inf"), device=dev)       # (an empty shard is a valid shard)
+    hi = tree_pos.max(dim=0).values if tree_pos.numel() else torch.full((3,), float("-inf"), device=dev)
+    cnt = torch.tensor([tree_pos.size(0)], dtype=torch.long, device=dev)
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
         dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)

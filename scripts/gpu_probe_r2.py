@@ -38,10 +38,10 @@ noisy, analytic, _ = bench.make_shard(args, n, dev, 0, 1)
 nrm = bench.single_gpu_normals(noisy, analytic)
 run("chunked", noisy, nrm)
 del noisy, nrm, analytic
-clean, normal = W.creased_surface(n, 1234, dev)
+sys.exit(0)
 sess = _lib.Session(clean, 16)
 s, c = sess.mean_edge_length_parts(6)
 del sess
 noisy = W.add_noise(clean, 0.3 * s / c * 6.0 / 5.0)
 nrm = bench.single_gpu_normals(noisy, normal)
-run("round1", noisy, nrm)
+pass

@@ -28,7 +28,7 @@ def main():
     kind = os.environ.get("NGPD_CHECK_SURFACE", "creased")
     sigma = 0.3 * W.mean_knn_distance(kind, n, 6)
 
-    def shard(r, w):
+    def shard(r, w, n=n, sigma=sigma):
         ps, ns, gs = [], [], []
         for c in W.chunks_of(n, r, w):
             p, q, g = W.surface_chunk(kind, n, c, 7, dev)
@@ -106,22 +106,15 @@ def main():
     # the benchmark's own recipe at a size where a cloud-wide sum has many terms: PCA normals computed per slab, more iterations
     n2 = int(os.environ.get("NGPD_CHECK_POINTS_2", 3000000))
     sigma2 = 0.3 * W.mean_knn_distance(kind, n2, 6)
-    ps, ns, gs = [], [], []
-    for c in W.chunks_of(n2, rank, world):
-        p, q, g = W.surface_chunk(kind, n2, c, 7, dev)
-        ps.append(W.noise_chunk(p, sigma2, c)); ns.append(q); gs.append(g)
-    slab = partition.SlabSession(torch.cat(ps), torch.cat(ns), k_f, 8, (1.0, 0.2, 1.0), shard_ids=torch.cat(gs))
+    ps, ns, gs = shard(rank, world, n2, sigma2)                 # (a rank may get no chunk at all: an empty shard is a valid shard)
+    slab = partition.SlabSession(ps, ns, k_f, 8, (1.0, 0.2, 1.0), shard_ids=gs)
     slab.pca_normals(12, orient_like="current")
     for _ in range(6):
         slab.step()
     csum = slab.checksum()
     need = slab.verify_halo()
     del slab, ps, ns, gs
-    ps, ns = [], []
-    for c in W.chunks_of(n2):
-        p, q, g = W.surface_chunk(kind, n2, c, 7, dev)
-        ps.append(W.noise_chunk(p, sigma2, c)); ns.append(q)
-    big, bign = torch.cat(ps), torch.cat(ns)
+    big, bign, _ = shard(0, 1, n2, sigma2)
     grid = _lib.Grid(big, 12)
     table = grid.knn(big, 12, _lib.KNN_SKIP_SELF | _lib.KNN_QUERY_IS_TREE)
     pn = torch.empty_like(big)

@@ -881,10 +881,16 @@ def test_cpsd_loop_vs_reference(ng, cpsd):
         bad_n = (angle_between(f_n.cpu().numpy(), cpsd[t + "f_n"]) > 1e-4).mean()
         err = np.abs(g.pos.cpu().numpy() - cpsd[t + "pos_out"]).max(axis=1) / scale
         print(f"\nCPSD iteration {it}: labels agree {agree:.4%}, normals > 1e-4 rad {bad_n:.4%}, positions > 1e-5 {(err > 1e-5).mean():.4%}")
-        # free-running: eigenvector signs feed the smoothing; the first iteration starts from identical inputs
-        assert agree > (0.999 if it == 0 else 0.97)
-        if it == 0:
-            assert bad_n < 0.01 and (err > 1e-5).mean() < 0.02
+        # Free-running: eigenvector signs feed the smoothing.  Yardstick (scripts/noise_floor_cpsd.py, three trials):
+        # the reference's own algorithm, re-run with its input normals moved by 1 ulp, agrees with itself on
+        #   labels      99.89-99.94 % / 99.74-99.77 % / 98.55-98.92 %   after iterations 1 / 2 / 3,
+        #   normals     0.37-0.42 %  / 1.9-2.4 %     / 6.7-8.8 %       further than 1e-4 rad,
+        #   positions   1.7-1.9 %    / 6.3-8.0 %     / 14.3-17.2 %     further than 1e-5 of the extent.
+        # The first iteration starts from identical inputs, so it must do better than that floor; the later ones must stay on it.
+        floor_labels, floor_normals, floor_pos = (0.9985, 0.9965, 0.9840)[it], (0.0045, 0.03, 0.10)[it], (0.021, 0.09, 0.20)[it]   # (three trials: a little slack)
+        assert agree > (0.999 if it == 0 else floor_labels), (it, agree)
+        assert bad_n < (0.01 if it == 0 else floor_normals), (it, bad_n)
+        assert (err > 1e-5).mean() < (0.02 if it == 0 else floor_pos), (it, (err > 1e-5).mean())
 
 
 def test_tensor_division_is_correctly_rounded(ng):
