@@ -393,9 +393,21 @@ def run_ours(args):
         slab = None
     else:
         slab = partition.SlabSession(noisy, analytic, K_F, K_U, ALPHAS, strategy=strategy, shard_ids=gids, flags=flags)
-        del noisy, analytic, gids
         slab.session.reserve(K_F)
         slab.pca_normals(12, orient_like="current")
+        balance = None
+        if not args.no_balance:
+            # cost-aware slab sizes (set-up, untimed): a three-iteration trial on a throw-away session measures every slab's kernel
+            # time, the slabs are cut again so that they cost the same, and the run starts over from the same input
+            t = slab.rank_costs(3)
+            fr = partition.rebalance_fractions(t, slab.plan.fractions)
+            balance = {"trial_kernel_ms_by_rank": [round(x, 4) for x in t], "point_fractions": [round(x, 5) for x in fr]}
+            del slab
+            torch.cuda.empty_cache()
+            slab = partition.SlabSession(noisy, analytic, K_F, K_U, ALPHAS, strategy=strategy, shard_ids=gids, flags=flags, fractions=fr)
+            slab.session.reserve(K_F)
+            slab.pca_normals(12, orient_like="current")
+        del noisy, analytic, gids
         if args.clamp:
             d = 2.0 * slab.mean_edge_length
             slab.params.dmax, slab.params.clamp_radius = d * 20000.0, d
@@ -436,6 +448,13 @@ def run_ours(args):
     ms = timed(args.steps)
     prof = profile_src.get_profile()
     profile_src.set_profiling(False)
+    by_rank = None
+    if world > 1:
+        # every rank's time per kernel group: the spread between the ranks is what the cross-rank rounds ("halo") wait for
+        mine = torch.tensor([prof[k][0] / args.steps for k in _lib.Session.PROFILE_NAMES], dtype=torch.float64, device=dev)
+        table = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(table, mine)
+        by_rank = {k: [round(float(t[i]), 4) for t in table] for i, k in enumerate(_lib.Session.PROFILE_NAMES)}
     # single GPU: the fused step restarts its counter, so the last step's count x steps; slabs likewise (one C call per step)
     launches = profile_src.launch_count() * args.steps
     clocks = sampler.stop() if sampler else None
@@ -451,7 +470,8 @@ def run_ours(args):
     else:
         digest = slab.checksum()
         need = slab.verify_halo()                               # raises if a slab search could have missed a foreign point
-        halo = {"halo_width": slab.plan.halo_width, "needed": need, "rows_owned_rank0": slab.n_owned, "rows_halo_rank0": slab.n_halo}
+        halo = {"halo_width": slab.plan.halo_width, "needed": need, "rows_owned_rank0": slab.n_owned, "rows_halo_rank0": slab.n_halo,
+                "balance": balance}
     names = _lib.Session.CHECKSUM_FIELDS
     checksum = {k: (f"{v:016x}" if k.endswith("hash") else (v - (1 << 64) if v >= (1 << 63) else v)) for k, v in zip(names, digest)}
     checksum["after_iterations"] = 2 + max(args.warmup - 2, 0) + args.steps
@@ -611,7 +631,7 @@ def run_ours(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, n), "clocks": clocks,
             "e2e": e2e, "cold": cold, "validated": validated, "checksum": checksum, "class_histogram": class_histogram, "halo": halo,
-            "knn": knn_line, "knn_tiers_last_step": knn_tiers, "extra_configs": extra, "gpu_launches": launches, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu}
+            "knn": knn_line, "knn_tiers_last_step": knn_tiers, "kernel_ms_per_step_by_rank": by_rank, "extra_configs": extra, "gpu_launches": launches, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu}
     print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -630,6 +650,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-knn", action="store_true")
     ap.add_argument("--no-validate", action="store_true")
+    ap.add_argument("--no-balance", action="store_true", help="N > 1: equal-size slabs instead of slabs of equal measured cost")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary single-GPU configurations (k = 32; dense-crease surface)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--k-feature", type=int, default=K_F, help="k of the feature pass (configs[2]: 32)")

@@ -54,8 +54,13 @@ struct KsCfg {
     // sheets of a surface meet (ncu round 2: the rows around the torus / cube-face intersection of the bench cloud) or with
     // k = 64 on cells sized for k <= 32, rows of 5 cells hold more than 64 points and 50 slots overflowed, which sent those
     // queries to the one-thread-per-query exact search (0.8 ms of latency per iteration for a few dozen rows).
+    // R = 2 also PRUNES: every slot carries a lower bound of its candidates' keys (distance from the query to the slot's cells), the
+    // rows of the inner 3x3 ring come first, and a slot whose bound is not below the lane's current threshold is skipped --
+    // a 5x5x5 block holds 750-900 candidates of which the outer shell (98 of 125 cells) almost never contributes, and the
+    // kernel's latency (one wave of blocks, 222 us whatever the cloud size) is the per-lane candidate count.
+    static constexpr bool PRUNE = R == 2;
     static constexpr int OFFBITS = R == 1 ? 6 : 7;
-    static constexpr int SLOTS = R == 1 ? 2 * ROWS : 64;
+    static constexpr int SLOTS = R == 1 ? 2 * ROWS : 56;
     static constexpr int SLOTBITS = R == 1 ? 5 : 6;
     static constexpr int IDBITS = SLOTBITS + OFFBITS;
     static constexpr unsigned IDMASK = (1u << IDBITS) - 1u;
@@ -67,7 +72,19 @@ template <int R>
 struct KsShared {
     int2 rng[KsCfg<R>::SLOTS][KsCfg<R>::THREADS];   // (first point, one past the last) of each slot
     unsigned batch[KS_BATCH][KsCfg<R>::THREADS];
+    unsigned mink[KsCfg<R>::PRUNE ? KsCfg<R>::SLOTS : 1][KsCfg<R>::THREADS];   // PRUNE: lower bound of the keys in the slot
 };
+
+// visiting order of the (dy, dz) rows of the block: the lane's own row first; R = 2: then the inner ring, then the outer ring
+template <int R>
+__device__ __forceinline__ int ks_row_order(int tt) {
+    constexpr int W = 2 * R + 1, MID = (W * W - 1) / 2;
+    if (R == 2) {
+        constexpr int order[25] = {12, 6, 7, 8, 11, 13, 16, 17, 18, 0, 1, 2, 3, 4, 5, 9, 10, 14, 15, 19, 20, 21, 22, 23, 24};
+        return order[tt];
+    }
+    return tt == 0 ? MID : (tt <= MID ? tt - 1 : tt);
+}
 
 // Near-ties: when the K-th and (K+1)-th candidates are closer together than the keys can tell, the first KF = K + 4
 // keys are re-evaluated exactly and the row is taken from those; only a list without spare entries (KT == K) has to
@@ -131,9 +148,16 @@ __device__ __forceinline__ bool knn_stream(KsTop<KT>& t, KsShared<R>& sm, const 
         constexpr int W = 2 * R + 1, MID = (C::ROWS - 1) / 2;
 #pragma unroll(R == 1 ? 9 : 5)
         for (int tt = 0; tt < C::ROWS; ++tt) {
-            const int o = tt == 0 ? MID : (tt <= MID ? tt - 1 : tt);      // (dy 0, dz 0) first
+            const int o = ks_row_order<R>(tt);                              // (dy 0, dz 0) first
             const int y = cy + (o % W) - R, z = cz + (o / W) - R;
             if ((unsigned)y >= (unsigned)g.ny || (unsigned)z >= (unsigned)g.nz) continue;
+            double gyz2 = 0.0;                                              // PRUNE: squared distance from the query to the row of cells
+            if (C::PRUNE) {
+                // (fp64 like the binning itself: in fp32 the offsets would carry 2e-5 h of error, more than the slack below)
+                const double fy = ry - (double)y * g.h, fz = rz - (double)z * g.h;                  // offsets from the cell's low faces
+                const double gy = fy < 0.0 ? -fy : (fy > g.h ? fy - g.h : 0.0), gz = fz < 0.0 ? -fz : (fz > g.h ? fz - g.h : 0.0);
+                gyz2 = gy * gy + gz * gz;
+            }
             const int64_t trow = ((int64_t)(z >> 3) * g.tby + (y >> 3)) * g.tbx;
             const int lrow = ((z & 7) << 6) | ((y & 7) << 3);
             int x0 = xa;
@@ -146,9 +170,19 @@ __device__ __forceinline__ bool knn_stream(KsTop<KT>& t, KsShared<R>& sm, const 
                     const int* f = g.fine + (int64_t)b * 513 + lrow;
                     int s = __ldg(f + (x0 & 7));
                     const int e = __ldg(f + (xe & 7) + 1);
+                    unsigned lowkey = 0;
+                    if (C::PRUNE) {
+                        // every point of cells x0 .. xe of this row is at least this far from the query; 1e-5 of relative slack covers the
+                        // fp32 evaluation of the candidates' own distances (a few 1e-7), the absolute term the binning (1e-13 h);
+                        // the key of a candidate is monotone in its distance, so no candidate of the slot has a smaller key
+                        const double fx0 = rx - (double)x0 * g.h, fx1 = rx - (double)(xe + 1) * g.h;
+                        const double gx = fx0 < 0.0 ? -fx0 : (fx1 > 0.0 ? fx1 : 0.0);
+                        const double lb = (gx * gx + gyz2) * (1.0 - 1e-5) - 1e-8 * g.h * g.h;
+                        lowkey = ks_dist_field<R>(lb > 0.0 ? (float)lb * 0.999999f : 0.0f, inv_h2);
+                    }
                     while (s < e) {                                    // one slot per 2^OFFBITS points
                         const int ee = min(e, s + (1 << C::OFFBITS));
-                        if (nr < C::SLOTS) { sm.rng[nr][tid] = make_int2(s, ee); ++nr; } else over = true;
+                        if (nr < C::SLOTS) { sm.rng[nr][tid] = make_int2(s, ee); if (C::PRUNE) sm.mink[nr][tid] = lowkey; ++nr; } else over = true;
                         s = ee;
                     }
                 }
@@ -187,8 +221,14 @@ __device__ __forceinline__ bool knn_stream(KsTop<KT>& t, KsShared<R>& sm, const 
         }
         rem -= KS_GROUP;
         if (rem > 0) { pp += KS_GROUP; idv += KS_GROUP; }
-        else if (r < nr) { int2 q = sm.rng[r][tid]; pp = g.pts + q.x; rem = q.y - q.x; idv = (unsigned)r << C::OFFBITS; ++r; }
-        else { pp = g.pts; rem = 0; }                                   // done: keep the speculative loads in bounds
+        else {
+            if (C::PRUNE) {
+                // slots none of whose candidates could be taken: they count as dropped at their lower bound
+                while (r < nr && sm.mink[r][tid] >= tau) { rej = min(rej, sm.mink[r][tid]); ++r; }
+            }
+            if (r < nr) { int2 q = sm.rng[r][tid]; pp = g.pts + q.x; rem = q.y - q.x; idv = (unsigned)r << C::OFFBITS; ++r; }
+            else { pp = g.pts; rem = 0; }                               // done: keep the speculative loads in bounds
+        }
         if (__any_sync(FULL, bp > b0 + (KS_BATCH - KS_GROUP) * C::THREADS)) {
             ks_round<KT, R>(t, sm, (int)(bp - b0) / C::THREADS, rej);
             bp = b0;

@@ -129,10 +129,10 @@ def _all_gather_var(t: torch.Tensor, world: int, group):
     return [b[:m] for b, m in zip(bufs, sizes)]
 
 
-def sample_splitters(keys: torch.Tensor, world: int, group, samples: int = 1 << 16) -> torch.Tensor:
-    """world - 1 Morton keys that cut the union of every rank's `keys` into world slabs of nearly equal size: every rank
-    contributes `samples` evenly spaced quantiles of its own keys, weighted by the rows each stands for, and the cuts are
-    read off the merged sample.  Imbalance <= world^2 / samples of a slab."""
+def sample_splitters(keys: torch.Tensor, world: int, group, samples: int = 1 << 16, fractions=None) -> torch.Tensor:
+    """world - 1 Morton keys that cut the union of every rank's `keys` into world slabs of nearly equal size (or of the given
+    `fractions` of the points): every rank contributes `samples` evenly spaced quantiles of its own keys, weighted by the rows
+    each stands for, and the cuts are read off the merged sample.  Imbalance <= world^2 / samples of a slab."""
     m = keys.numel()
     srt = torch.sort(keys).values
     take = min(samples, m)
@@ -146,9 +146,47 @@ def sample_splitters(keys: torch.Tensor, world: int, group, samples: int = 1 << 
     o = torch.argsort(all_s, stable=True)
     all_s, cum = all_s[o], torch.cumsum(all_w[o], 0)
     total = float(cum[-1]) if cum.numel() else 0.0
-    targets = torch.tensor([total * r / world for r in range(1, world)], dtype=torch.float64, device=keys.device)
+    if fractions is None:
+        fractions = [1.0 / world] * world
+    assert len(fractions) == world and min(fractions) > 0
+    norm, run, cuts = float(sum(fractions)), 0.0, []
+    for f in list(fractions)[:-1]:
+        run += float(f) / norm
+        cuts.append(total * run)
+    targets = torch.tensor(cuts, dtype=torch.float64, device=keys.device)
     at = torch.searchsorted(cum, targets).clamp_(max=max(all_s.numel() - 1, 0))
     return all_s[at] if all_s.numel() else torch.zeros(world - 1, dtype=torch.long, device=keys.device)
+
+
+def rebalance_fractions(times, fractions, damping: float = 1.0):
+    """Cost-aware slab sizes.  `times[r]` = measured kernel time of the slab that held `fractions[r]` of the points (slabs are
+    contiguous in Morton order): taking the cost per point as constant inside each old slab, returns the fractions whose
+    slabs all cost the same.  (The cost of a row varies by region -- rows that leave the re-ranking tier of the k-NN cost
+    ~20 x, crease rows take the LAPACK-order path and the listed-rows updates -- and the phases of an iteration are separated
+    by cross-rank rounds, so the slowest slab sets the pace.)  damping < 1 moves only part of the way."""
+    world = len(times)
+    tot_f = float(sum(fractions))
+    f = [float(x) / tot_f for x in fractions]
+    t = [max(float(x), 1e-12) for x in times]
+    total, target = sum(t), sum(t) / world
+    # piecewise-linear cumulative cost over the point coordinate x in [0, 1]; invert it at j * total / world
+    edges_x, edges_c = [0.0], [0.0]
+    for fr, tr in zip(f, t):
+        edges_x.append(edges_x[-1] + fr)
+        edges_c.append(edges_c[-1] + tr)
+    cuts = [0.0]
+    seg = 0
+    for j in range(1, world):
+        c = j * target
+        while seg < world - 1 and edges_c[seg + 1] < c:
+            seg += 1
+        a = (c - edges_c[seg]) / (edges_c[seg + 1] - edges_c[seg])
+        cuts.append(edges_x[seg] + a * (edges_x[seg + 1] - edges_x[seg]))
+    cuts.append(1.0)
+    new = [cuts[j + 1] - cuts[j] for j in range(world)]
+    out = [(1.0 - damping) * o + damping * nw for o, nw in zip(f, new)]
+    s_ = sum(out)
+    return [x / s_ for x in out]
 
 
 class ShardedSlabPlan:
@@ -159,11 +197,12 @@ class ShardedSlabPlan:
     Fields as SlabPlan (`owned`, `halo`, `local_ids` hold global ids) plus the routed data: `tree_local` [n_owned + n_halo, 3]
     and `payload_local`, and the halo wiring itself (`send_local`, `recv_counts`), so HaloExchanger needs no request round."""
 
-    def __init__(self, tree_pos: torch.Tensor, gids: torch.Tensor, halo_width: float, group=None, payload=()):
+    def __init__(self, tree_pos: torch.Tensor, gids: torch.Tensor, halo_width: float, group=None, payload=(), fractions=None):
         world = dist.get_world_size(group) if dist.is_initialized() else 1
         rank = dist.get_rank(group) if dist.is_initialized() else 0
         dev = tree_pos.device
         self.rank, self.world, self.halo_width = rank, world, float(halo_width)
+        self.fractions = list(fractions) if fractions is not None else [1.0 / world] * world
         lo = tree_pos.min(dim=0).values if tree_pos.numel() else torch.full((3,), float("inf"), device=dev)
         hi = tree_pos.max(dim=0).values if tree_pos.numel() else torch.full((3,), float("-inf"), device=dev)
         cnt = torch.tensor([tree_pos.size(0)], dtype=torch.long, device=dev)
@@ -176,7 +215,7 @@ class ShardedSlabPlan:
         keys = morton_keys(tree_pos, lo, hi)
         data = [gids.long(), tree_pos] + list(payload)
         if world > 1:
-            self.splitters = sample_splitters(keys, world, group)
+            self.splitters = sample_splitters(keys, world, group, fractions=fractions)
             dest = torch.bucketize(keys, self.splitters, right=True)
             del keys
             data, _ = _route(data, dest, world, group)
@@ -378,11 +417,12 @@ class SlabSession:
     def __init__(self, pos: torch.Tensor, nrm: torch.Tensor | None, k_feature=16, k_update=8, alphas=(1.0, 0.2, 1.0),
                  strategy=None, halo_width: float | None = None, group=None, tree_pos: torch.Tensor | None = None,
                  transport: str | None = None, shard_ids: torch.Tensor | None = None, mean_edge_length: float | None = None,
-                 flags: int = 0, clamp_radius: float = 0.0):
+                 flags: int = 0, clamp_radius: float = 0.0, fractions=None):
         """Replicated input (shard_ids None): every rank passes the WHOLE cloud and keeps its slab (small clouds, tests).
         Sharded input: every rank passes any part of the cloud with the points' global ids in `shard_ids`; rows are routed
         to their slabs (ShardedSlabPlan) and no rank holds more than shard + slab + halo.  nrm None: normals are set later
-        (set_owned_normals / pca_normals)."""
+        (set_owned_normals / pca_normals).  fractions (sharded input): share of the points per slab, e.g. from
+        rebalance_fractions() after a trial run; default equal."""
         from . import _lib
         self._lib = _lib
         self.group = group
@@ -397,7 +437,7 @@ class SlabSession:
         else:
             hw = halo_width if halo_width is not None else estimate_halo_width_sharded(tree, k_feature, group)
             payload = ([pos] if tree_pos is not None else []) + ([nrm] if nrm is not None else [])
-            self.plan = ShardedSlabPlan(tree, shard_ids, hw, group, payload)
+            self.plan = ShardedSlabPlan(tree, shard_ids, hw, group, payload, fractions)
             tree_l = self.plan.tree_local.contiguous()
             rest = list(self.plan.payload_local)
             pos_l = rest.pop(0).contiguous() if tree_pos is not None else tree_l
@@ -561,6 +601,24 @@ class SlabSession:
             L.check(lib.ngpd_session_phase_update(h, ref, key, st()), "phase_update")
             self._refresh(0)                                    # the class' new positions, before the next class reads them
         L.check(lib.ngpd_session_phase_commit_normals(h), "commit normals")
+
+    def rank_costs(self, steps: int = 3):
+        """Runs `steps` iterations with the kernel timers on and returns every rank's kernel time per step (ms), the cross-rank
+        rounds excluded -- what rebalance_fractions() wants.  The state advances; use a throw-away session."""
+        s = self.session
+        s.set_profiling(True)
+        s.get_profile()
+        for _ in range(steps):
+            self.step()
+        prof = s.get_profile()
+        s.set_profiling(False)
+        mine = torch.tensor([sum(v[0] for k, v in prof.items() if k != "halo") / steps], dtype=torch.float64, device=self._send_buf.device)
+        table = [torch.empty_like(mine) for _ in range(self.world)]
+        if self.world > 1:
+            dist.all_gather(table, mine, group=self.group)
+        else:
+            table = [mine]
+        return [float(t.item()) for t in table]
 
     def verify_halo(self) -> float:
         """The slab searches equal the whole cloud's iff every owned row's (k-th neighbour distance + displacement from its

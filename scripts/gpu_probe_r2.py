@@ -30,7 +30,7 @@ def run(name, noisy, nrm, steps=8):
         st = sess.knn_stats()
         d = sess.checksum()
         print(f"{name} it {it}: {e0.elapsed_time(e1):.3f} ms  " + " ".join(f"{k}={v[0]:.3f}" for k, v in prof.items() if v[1]) +
-              f"  tiers(t0->search, t1->t2, t2->exact)={st}  labels={d[6:9]}", flush=True)
+              f"  tiers(t0->search, t1->t2, t2->exact)={st}  labels={d[6:9]} hash={d[0]:016x}/{d[1]:016x}", flush=True)
 
 
 args = argparse.Namespace(surface="creased", strategy="flat/edge/feature", clamp=False)

@@ -233,6 +233,16 @@ def _sharded_worker(rank, world, port, out):
             state[torch.cat(ex.recv_local)] = recv
             assert torch.equal(state, values(plan.local_ids, phase)), f"phase {phase}"
 
+        # 3b. cost-aware slab sizes: the slabs follow the requested shares of the points, rebalance_fractions() inverts a
+        #     piecewise-constant cost density
+        plan2 = partition.ShardedSlabPlan(shard, gid, hw, None, [], fractions=[0.3, 0.7])
+        sizes = [None] * world
+        dist.all_gather_object(sizes, plan2.n_owned)
+        assert sum(sizes) == n and abs(sizes[0] - 0.3 * n) < 0.02 * n
+        assert np.allclose(partition.rebalance_fractions([1, 3], [0.5, 0.5]), [2 / 3, 1 / 3])
+        assert np.allclose(partition.rebalance_fractions([1, 1, 2, 2], [0.25] * 4), [0.375, 0.25, 0.1875, 0.1875])
+        assert np.allclose(partition.rebalance_fractions([2, 2, 2], [0.2, 0.3, 0.5]), [0.2, 0.3, 0.5])
+
         # 4. peer-push addressing agrees between the ranks (what _wire_peer hands to ngpd_session_set_slab)
         cap, first_row, seg = ex.peer_layout(torch.device("cpu"))
         caps = [None] * world
