@@ -397,9 +397,9 @@ def run_ours(args):
         slab.pca_normals(12, orient_like="current")
         balance = None
         if not args.no_balance:
-            # cost-aware slab sizes (set-up, untimed): a three-iteration trial on a throw-away session measures every slab's kernel
-            # time, the slabs are cut again so that they cost the same, and the run starts over from the same input
-            t = slab.rank_costs(3)
+            # cost-aware slab sizes (set-up, untimed): a trial on a throw-away session (2 + 3 iterations, the last 3 measured) gives every
+            # slab's kernel time, the slabs are cut again so that they cost the same, and the run starts over from the same input
+            t = slab.rank_costs(3, 2)
             fr = partition.rebalance_fractions(t, slab.plan.fractions)
             balance = {"trial_kernel_ms_by_rank": [round(x, 4) for x in t], "point_fractions": [round(x, 5) for x in fr]}
             del slab

@@ -602,10 +602,14 @@ class SlabSession:
             self._refresh(0)                                    # the class' new positions, before the next class reads them
         L.check(lib.ngpd_session_phase_commit_normals(h), "commit normals")
 
-    def rank_costs(self, steps: int = 3):
-        """Runs `steps` iterations with the kernel timers on and returns every rank's kernel time per step (ms), the cross-rank
-        rounds excluded -- what rebalance_fractions() wants.  The state advances; use a throw-away session."""
+    def rank_costs(self, steps: int = 3, skip: int = 2):
+        """Runs `skip` + `steps` iterations and returns every rank's kernel time per step (ms) over the last `steps`, the
+        cross-rank rounds excluded -- what rebalance_fractions() wants.  The first iterations are skipped because their search
+        has no stored candidates and costs several times a steady-state one, with another distribution over the cloud.
+        The state advances; use a throw-away session."""
         s = self.session
+        for _ in range(skip):
+            self.step()
         s.set_profiling(True)
         s.get_profile()
         for _ in range(steps):
