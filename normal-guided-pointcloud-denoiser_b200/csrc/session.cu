@@ -17,6 +17,9 @@
 #include "point_math.cuh"
 #include "../../include/ngpd.h"
 
+#ifndef NGPD_CLASSIFY_BLOCKS
+#define NGPD_CLASSIFY_BLOCKS 9   // resident blocks per SM of the stage-2 kernel at k = 16 (56 registers); 8 = 64 registers measured in profiles/
+#endif
 #define NGPD_PROF_CATEGORIES 6   // 0 knn, 1 nvt+smooth, 2 nvt+classify, 3 flat scalars, 4 update, 5 halo exchange + cross-rank scalars (multi-GPU)
 
 namespace ngpd {
@@ -68,7 +71,12 @@ struct ngpd_session {
     long long* part = nullptr;  // [cdiv(n,128) * 4], fixed point (sum_scale)
     float sum_scale = 1.0f;     // power of two: a row's neighbour-position sum times this is < 2^32 in magnitude
     double* red2 = nullptr;     // scratch of the two-level reduction (slice sums + ticket counter)
-    bool sums_ready = false;  // part[] describes the current positions and labels
+    bool sums_ready = false;  // part[] and blockfar[] describe the current positions and labels
+    // flat_step's delta without a second pass over the cloud: the stage-2 kernel also leaves, per block, the largest distance of
+    // the class' neighbours from a REFERENCE centre (the previous iteration's); once the true centre is known only the blocks that
+    // can still hold the farthest point are looked at again (session_class_max_pruned_kernel)
+    float* blockfar = nullptr;  // [cdiv(n,128)] squared distances, + [1] their maximum (uint bits, atomicMax)
+    float* cref = nullptr;      // reference centre xyz, [3] = distance between it and the centre now in cd
     // rows of classes 1 and 2 (the minorities: creases and corners), listed by the stage-2 kernel so that their updates
     // touch only their own rows instead of streaming the whole cloud through once more: [2 * n rows][2 counters]
     int32_t* cls = nullptr;
@@ -482,14 +490,15 @@ __global__ void __launch_bounds__(128) session_nvt_smooth_late_kernel(Quad4 pos,
 // direction (edge_mask: bit l set = rows labelled l are moved by edge_step), and every row when FAST is off go through the
 // LAPACK-order solver.
 template <int K, bool FAST>
-__global__ void __launch_bounds__(128, K == 16 ? 9 : (K == 32 ? 6 : 1)) session_nvt_classify_kernel(Quad4 pos, Quad4 fn, const uint8_t* __restrict__ owned,
+__global__ void __launch_bounds__(128, K == 16 ? NGPD_CLASSIFY_BLOCKS : (K == 32 ? 6 : 1)) session_nvt_classify_kernel(Quad4 pos, Quad4 fn, const uint8_t* __restrict__ owned,
                                                                    const int32_t* __restrict__ idx, int64_t n, int k, float x_thresh,
                                                                    float scale, uint8_t* __restrict__ label, float4* __restrict__ edge, int edge_mask,
                                                                    int sum_key, int ku, long long* __restrict__ part, float sum_scale,
+                                                                   const float* __restrict__ cref, float* __restrict__ blockfar,
                                                                    int32_t* __restrict__ cls) {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = s < n && (!owned || owned[s]);
-    float fx = 0.0f, fy = 0.0f, fz = 0.0f;
+    float fx = 0.0f, fy = 0.0f, fz = 0.0f, far2 = 0.0f;
     int lab = -1;
     if (active) {
         // the sum of the first ku neighbour positions (flat_step's centre) is accumulated inside the vote loop, where the
@@ -499,9 +508,10 @@ __global__ void __launch_bounds__(128, K == 16 ? 9 : (K == 32 ? 6 : 1)) session_
         if (K > 0) {
             RowRegs<K> row;
             row.load(idx + s * K);
-            nvt_tensor_row<K>(pos, fn, s, row, idx + s * K, K, x_thresh, t6, part ? &ps : nullptr, ku);
+            nvt_tensor_row<K>(pos, fn, s, row, idx + s * K, K, x_thresh, t6, part ? &ps : nullptr, ku, cref, part ? &far2 : nullptr);
         } else {
-            nvt_tensor_row<0>(pos, fn, s, RowPtr<int32_t>{idx + s * k}, idx + s * k, k, x_thresh, t6, part ? &ps : nullptr, ku);
+            nvt_tensor_row<0>(pos, fn, s, RowPtr<int32_t>{idx + s * k}, idx + s * k, k, x_thresh, t6, part ? &ps : nullptr, ku, cref,
+                              part ? &far2 : nullptr);
         }
         V3 y = v3(0.0f, 0.0f, 0.0f);
         bool full = !FAST;
@@ -533,10 +543,18 @@ __global__ void __launch_bounds__(128, K == 16 ? 9 : (K == 32 ? 6 : 1)) session_
             qx += __shfl_xor_sync(0xffffffffu, qx, o); qy += __shfl_xor_sync(0xffffffffu, qy, o); qz += __shfl_xor_sync(0xffffffffu, qz, o);
         }
         const int w = threadIdx.x >> 5;
-        if ((threadIdx.x & 31) == 0) { red[w][0] = qx; red[w][1] = qy; red[w][2] = qz; red[w][3] = (long long)ku * __popc(members); }
+        // (squared distances are non-negative floats: their bit patterns order like the values)
+        __shared__ unsigned farw[4];
+        const unsigned fm = __reduce_max_sync(0xffffffffu, lab == sum_key ? __float_as_uint(far2) : 0u);
+        if ((threadIdx.x & 31) == 0) { red[w][0] = qx; red[w][1] = qy; red[w][2] = qz; red[w][3] = (long long)ku * __popc(members); farw[w] = fm; }
         __syncthreads();
         if (threadIdx.x < 4)
             part[(int64_t)blockIdx.x * 4 + threadIdx.x] = ((red[0][threadIdx.x] + red[1][threadIdx.x]) + red[2][threadIdx.x]) + red[3][threadIdx.x];
+        if (threadIdx.x == 0 && blockfar) {
+            const unsigned m = max(max(farw[0], farw[1]), max(farw[2], farw[3]));
+            blockfar[blockIdx.x] = __uint_as_float(m);
+            if (m) atomicMax(reinterpret_cast<unsigned*>(blockfar + gridDim.x), m);
+        }
     }
     if (cls) {
         // block-aggregated append to the two class lists: one global atomic per block and class
@@ -632,10 +650,48 @@ __global__ void __launch_bounds__(256) session_class_sum_kernel(Quad4 pos, const
         part[(int64_t)blockIdx.x * 4 + threadIdx.x] = t;
     }
 }
-// acc = {sum x, sum y, sum z in units of 1 / sum_scale, neighbour count} -> centre
-__global__ void session_center_kernel(const long long* __restrict__ acc, float sum_scale, float* __restrict__ cd) {
+// acc = {sum x, sum y, sum z in units of 1 / sum_scale, neighbour count} -> centre.  cref (nullable): the reference centre the last
+// stage-2 pass measured its per-block maxima from; receives its distance from the new centre ([3], rounded up) and then the new centre
+// itself, which is the next iteration's reference.
+__global__ void session_center_kernel(const long long* __restrict__ acc, float sum_scale, float* __restrict__ cd, float* __restrict__ cref) {
     const double c = acc[3] > 0 ? (double)acc[3] * (double)sum_scale : 1.0;
-    cd[0] = (float)((double)acc[0] / c); cd[1] = (float)((double)acc[1] / c); cd[2] = (float)((double)acc[2] / c); cd[3] = 0.0f;
+    const float x = (float)((double)acc[0] / c), y = (float)((double)acc[1] / c), z = (float)((double)acc[2] / c);
+    cd[0] = x; cd[1] = y; cd[2] = z; cd[3] = 0.0f;
+    if (cref) {
+        const double dx = (double)x - cref[0], dy = (double)y - cref[1], dz = (double)z - cref[2];
+        cref[3] = (float)(sqrt(dx * dx + dy * dy + dz * dz) * 1.0001) + 1e-30f;
+        cref[0] = x; cref[1] = y; cref[2] = z;
+    }
+}
+// flat_step's delta (Denoiser.py:107) from the per-block maxima of the stage-2 pass.  far2[b] = largest squared distance of block b's
+// class neighbours from the REFERENCE centre, far2[blocks] = the largest of them all (d'max^2), eps = |centre - reference|.
+// The neighbour farthest from the true centre (distance delta) is at least delta - eps from the reference, and delta >= d'max - eps:
+// only blocks with far[b] >= d'max - 2 eps can hold it.  Those are recomputed exactly as the full pass would (same arithmetic, same
+// atomicMax), every other block costs one 4-byte load per warp.  One warp per 128-row block.
+__global__ void __launch_bounds__(256) session_class_max_pruned_kernel(Quad4 pos, const uint8_t* __restrict__ owned, const uint8_t* __restrict__ label,
+                                                                       int key, const int32_t* __restrict__ idx, int64_t n, int k, int ku,
+                                                                       const float* __restrict__ far2, int64_t blocks, const float* __restrict__ cref,
+                                                                       float* __restrict__ cd) {
+    const V3 c = v3(cd[0], cd[1], cd[2]);
+    const float eps = cref[3];
+    const float thr = sqrtf(far2[blocks]) * 0.99999f - 2.0f * eps;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    float mx = 0.0f;
+    for (int64_t b = warp; b < blocks; b += warps) {
+        const float f = __ldg(far2 + b);
+        if (!(sqrtf(f) >= thr) || f == 0.0f) continue;              // (f == 0: no row of the class in the block)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int64_t s = b * 128 + lane + 32 * i;
+            if (s >= n || (owned && !owned[s]) || label[s] != key) continue;
+            const int32_t* row = idx + s * k;
+            for (int a = 0; a < ku; ++a) mx = fmaxf(mx, norm3_fma(pos((int64_t)row[a]) - c));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0 && mx > 0.0f) atomicMax((int*)(cd + 3), __float_as_int(mx));
 }
 __global__ void __launch_bounds__(256) session_class_max_kernel(Quad4 pos, const uint8_t* __restrict__ owned, const uint8_t* __restrict__ label,
                                                                 int key, const int32_t* __restrict__ idx, int64_t n, int k, int ku,
@@ -1076,7 +1132,7 @@ static int slab_flush(ngpd_session_t* S, cudaStream_t st);
 extern "C" __attribute__((visibility("default"))) int ngpd_session_destroy(ngpd_session_t* S) {
     if (!S) return 0;
     if (S->grid) ngpd_grid_destroy(S->grid);
-    void* bufs[] = {S->pos[0], S->pos[1], S->nrm, S->fn, S->edge, S->label, S->owned, S->idx, S->acc, S->cd, S->fix, S->cand, S->anchor, S->part, S->red2, S->cls, S->inv, S->stage_pos, S->stage_nrm, S->stage_lab, S->orig};
+    void* bufs[] = {S->pos[0], S->pos[1], S->nrm, S->fn, S->edge, S->label, S->owned, S->idx, S->acc, S->cd, S->fix, S->cand, S->anchor, S->part, S->red2, S->cls, S->inv, S->stage_pos, S->stage_nrm, S->stage_lab, S->orig, S->blockfar, S->cref};
     for (void* b : bufs) if (b) cudaFree(b);
     if (S->side) { cudaStreamDestroy(S->side); for (cudaEvent_t e : S->xfer) if (e) cudaEventDestroy(e); }
     if (S->tail) { cudaStreamDestroy(S->tail); for (cudaEvent_t e : S->tail_ev) if (e) cudaEventDestroy(e); }
@@ -1116,10 +1172,17 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_create(const 
     if (e == cudaSuccess) e = cudaMalloc(&S->label, (size_t)n);
     if (e == cudaSuccess) e = cudaMalloc(&S->acc, 4 * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&S->cd, 4 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&S->cref, 4 * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&S->red2, (RED_BLOCKS * 4 + 1) * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&S->fix, (3 * (size_t)n + 3) * sizeof(int32_t));
     if (e != cudaSuccess) { set_error("ngpd_session_create: %s", cudaGetErrorString(e)); ngpd_session_destroy(S); return -2; }
     NGPD_CUDA_OK(cudaMemsetAsync(S->label, 0, (size_t)n, st));
+    {
+        // first reference centre of flat_step's pruned delta pass: the middle of the tree's bounding box (any point is valid)
+        const float c0[4] = {0.5f * (G->bbox[0] + G->bbox[3]), 0.5f * (G->bbox[1] + G->bbox[4]), 0.5f * (G->bbox[2] + G->bbox[5]), 0.0f};
+        NGPD_CUDA_OK(cudaMemcpyAsync(S->cref, c0, sizeof(c0), cudaMemcpyHostToDevice, st));
+        NGPD_CUDA_OK(cudaStreamSynchronize(st));
+    }
     NGPD_CUDA_OK(cudaMemsetAsync(S->red2, 0, (RED_BLOCKS * 4 + 1) * sizeof(double), st));
     NGPD_CUDA_OK(cudaMemsetAsync(S->nrm, 0, b4, st));
     // current positions start as the tree positions
@@ -1198,6 +1261,7 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_reserve(ngpd_
         if ((rc = reserve_candidates(S, K, st))) return rc;
     }
     if (!S->part) NGPD_CUDA_OK(cudaMalloc(&S->part, (size_t)cdiv(S->n, 128) * 4 * sizeof(long long)));
+    if (!S->blockfar) NGPD_CUDA_OK(cudaMalloc(&S->blockfar, ((size_t)cdiv(S->n, 128) + 1) * sizeof(float)));
     if (!S->cls) NGPD_CUDA_OK(cudaMalloc(&S->cls, (2 * (size_t)S->n + 2) * sizeof(int32_t)));
     return 0;
 }
@@ -1272,6 +1336,8 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_phase_feature
         if (p->strategy[0] == NGPD_STEP_FLAT) {
             if (!S->part) NGPD_CUDA_OK(cudaMalloc(&S->part, (size_t)b * 4 * sizeof(long long)));
             part = S->part;
+            if (!S->blockfar) NGPD_CUDA_OK(cudaMalloc(&S->blockfar, ((size_t)b + 1) * sizeof(float)));
+            NGPD_CUDA_OK(cudaMemsetAsync(S->blockfar + b, 0, sizeof(float), st));
         }
         S->sums_ready = part != nullptr;
         if (!S->cls) NGPD_CUDA_OK(cudaMalloc(&S->cls, (2 * (size_t)S->n + 2) * sizeof(int32_t)));
@@ -1286,7 +1352,7 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_phase_feature
         const bool fast = !fast_off && (edge_mask & 1) == 0;
         { ProfScope ps(S, st, 2);
           Quad4 fq{S->fn};
-#define NGPD_CLASSIFY(KK, FF) session_nvt_classify_kernel<KK, FF><<<b, 128, 0, st>>>(pos, fq, S->owned, S->idx, S->n, kf, p->x_thresh, p->scale, S->label, S->edge, edge_mask, 0, p->k_update, part, S->sum_scale, cls)
+#define NGPD_CLASSIFY(KK, FF) session_nvt_classify_kernel<KK, FF><<<b, 128, 0, st>>>(pos, fq, S->owned, S->idx, S->n, kf, p->x_thresh, p->scale, S->label, S->edge, edge_mask, 0, p->k_update, part, S->sum_scale, S->cref, part ? S->blockfar : nullptr, cls)
           if (fast) {
               if (kf == 16) NGPD_CLASSIFY(16, true); else if (kf == 32) NGPD_CLASSIFY(32, true); else if (kf == 8) NGPD_CLASSIFY(8, true); else NGPD_CLASSIFY(0, true);
           } else {
@@ -1323,8 +1389,16 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_phase_flat_sc
         S->sums_ready = false;
         S->launches += 2;
     } else {
-        session_center_kernel<<<1, 1, 0, st>>>(reinterpret_cast<const long long*>(S->acc), S->sum_scale, S->cd);
-        session_class_max_kernel<<<strided(S->n, 256), 256, 0, st>>>(pos, S->owned, S->label, key, S->idx, S->n, S->idx_k, p->k_update, S->cd);
+        static const bool full_pass = getenv("NGPD_DELTA_FULL_PASS") != nullptr;   // A/B measurements: round 1's pass over every row
+        if (key == 0 && S->sums_ready && S->blockfar && !full_pass) {
+            // the stage-2 kernel left per-block maxima: only the blocks that can hold the farthest neighbour are looked at again
+            session_center_kernel<<<1, 1, 0, st>>>(reinterpret_cast<const long long*>(S->acc), S->sum_scale, S->cd, S->cref);
+            session_class_max_pruned_kernel<<<strided(cdiv(S->n, 128) * 32, 256), 256, 0, st>>>(pos, S->owned, S->label, key, S->idx, S->n, S->idx_k, p->k_update,
+                                                                                                S->blockfar, cdiv(S->n, 128), S->cref, S->cd);
+        } else {
+            session_center_kernel<<<1, 1, 0, st>>>(reinterpret_cast<const long long*>(S->acc), S->sum_scale, S->cd, nullptr);
+            session_class_max_kernel<<<strided(S->n, 256), 256, 0, st>>>(pos, S->owned, S->label, key, S->idx, S->n, S->idx_k, p->k_update, S->cd);
+        }
         S->launches += 2;
     }
     NGPD_CUDA_OK(cudaGetLastError());

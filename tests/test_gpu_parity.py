@@ -1178,3 +1178,46 @@ def test_sampler_and_noise_on_device(ng, tmp_path):
     along = (off * pc.n).sum(1)
     assert float((off - along[:, None] * pc.n).abs().max()) < 1e-6
     assert abs(float(along.std()) - 0.003) < 3e-5 and abs(float(along.mean())) < 2e-5
+
+
+def test_pruned_delta_pass_is_exact(ng):
+    """flat_step's delta (Denoiser.py:107) from the per-block maxima of the stage-2 pass + a look at the candidate blocks only
+    (session_class_max_pruned_kernel) must be the exact maximum over the class-0 neighbour multiset, in every iteration -- the
+    reference centre it prunes with is the previous iteration's (the bounding-box centre the first time)."""
+    import ctypes
+    L = ng._lib
+    lib = L.load()
+    n = 300000
+    pts = cu(surface_cloud(n, seed=5, noise=0.003))
+    # off-centre cloud: the bounding-box centre is far from the centroid, so the first iteration prunes with a poor reference
+    pts = torch.cat([pts, pts[:20000] * 0.1 + torch.tensor([4.0, 0.5, -0.25], device="cuda")]).contiguous()
+    n = pts.size(0)
+    nrm = torch.nn.functional.normalize(torch.randn((n, 3), generator=torch.Generator().manual_seed(3)), dim=1).cuda()
+    sess = L.Session(pts, 16)
+    sess.set_state(pts, nrm)
+    s, c = sess.mean_edge_length_parts(6)
+    params = L.make_params(dmax=2.0 * s / c)
+    ref = ctypes.byref(params)
+    view = lambda which, shape, ts: torch.as_tensor(type("V", (), {"__cuda_array_interface__": {"data": (int(lib.ngpd_session_buffer(sess._h, which)), False),
+                                                                                           "shape": shape, "typestr": ts, "version": 2}})(), device="cuda")
+    perm = sess.order().long()
+    for it in range(4):
+        L.check(lib.ngpd_session_phase_features(sess._h, ref, 0, L.stream()), "f0")
+        L.check(lib.ngpd_session_phase_features(sess._h, ref, 1, L.stream()), "f1")
+        L.check(lib.ngpd_session_phase_flat_scalars(sess._h, ref, 0, 0, L.stream()), "s0")
+        L.check(lib.ngpd_session_phase_flat_scalars(sess._h, ref, 0, 1, L.stream()), "s1")
+        cd = view(4, (4,), "<f4").clone()
+        lab = view(5, (n,), "|u1")
+        idx = view(6, (n, 16), "<i4")
+        pos4 = view(0, (n, 4), "<f4")
+        rows = (lab == 0).nonzero().flatten()
+        nb = idx[rows][:, :8].long().reshape(-1)
+        d = pos4[nb, :3] - cd[:3]
+        # torch's norm of 3 components on the GPU is not the fma chain the kernels (and torch-CPU) use: compare with a relative bound
+        exact = float(d.double().norm(dim=1).max())
+        centre = pos4[nb, :3].double().mean(0)
+        assert float((centre - cd[:3].double()).abs().max()) < 1e-6 * float(pts.abs().max())
+        assert abs(float(cd[3]) - exact) <= 2e-7 * exact, (it, float(cd[3]), exact)
+        for key in range(3):
+            L.check(lib.ngpd_session_phase_update(sess._h, ref, key, L.stream()), "u")
+        L.check(lib.ngpd_session_phase_commit_normals(sess._h), "c")
