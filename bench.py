@@ -37,7 +37,8 @@ def algorithmic_bytes(k_f=None, k_u=None):
         "knn": 12 + 12 + 4 * k_f,                    # query, tree point, neighbour row out
         "nvt_smooth": 4 * k_f + 12 + 12 + 12,        # row in, position, normal, smoothed normal out
         "nvt_classify": 4 * k_f + 12 + 12 + 1 + 12,  # row in, position, smoothed normal, label + crease vector out
-        "flat_scalars": 2 * (4 * k_u + 1),           # two passes over the class' rows (gathers are cache hits)
+        "flat_scalars": None,                        # SURVEY 8(d) counts two passes over the class' rows (2 x (4 k_u + 1) B); the sums ride in the
+                                                     # stage-2 kernel and delta comes from its per-block maxima: no pass over the rows is left to rate
         "update": 4 * k_u + 12 + 12 + 1 + 12 + 12,   # phase C of 8(d), all three class launches together
         "iteration": 134 + 8 * k_f + 4 * k_u,
     }
@@ -602,12 +603,14 @@ def run_ours(args):
             continue
         per_step = tms / args.steps
         entry = {"ms_per_step": per_step, "launches_per_step": cnt / args.steps, "share_of_step": per_step / step_ms}
-        if name in bytes_per:
+        if bytes_per.get(name) is not None:
             ab = bytes_per[name] * n_local
             entry.update({"algorithmic_bytes_per_point": bytes_per[name], "achieved_gbs": ab / (per_step * 1e-3) / 1e9,
                           "frac": ab / (per_step * 1e-3) / 1e9 / peak})
-        else:
+        elif name == "halo":
             entry["note"] = "halo refreshes + cross-rank scalars; includes waiting for the slowest peer"
+        else:
+            entry["note"] = "flat_step's centre / delta: reduction of per-block sums and maxima left by the stage-2 kernel + the candidate blocks"
         kernels[name] = entry
     kernel_ms = sum(v["ms_per_step"] for v in kernels.values())
     dom = max((k for k in kernels if "frac" in kernels[k]), key=lambda k: kernels[k]["ms_per_step"])

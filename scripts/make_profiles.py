@@ -19,7 +19,10 @@ if os.path.exists(bench):
         out.append(f"* cpu_baseline: {d['cpu_baseline']}")
     out.append("\n| kernel group | ms/step | launches/step | algorithmic B/point | achieved GB/s | frac of HBM peak | share of step |\n|---|---|---|---|---|---|---|")
     for k, v in d["kernels"].items():
-        out.append(f"| {k} | {v['ms_per_step']:.3f} | {v['launches_per_step']:.0f} | {v['algorithmic_bytes_per_point']} | {v['achieved_gbs']:.0f} | {v['frac']:.3f} | {v['share_of_step']:.3f} |")
+        if "frac" in v:
+            out.append(f"| {k} | {v['ms_per_step']:.3f} | {v['launches_per_step']:.0f} | {v['algorithmic_bytes_per_point']} | {v['achieved_gbs']:.0f} | {v['frac']:.3f} | {v['share_of_step']:.3f} |")
+        else:
+            out.append(f"| {k} | {v['ms_per_step']:.3f} | {v['launches_per_step']:.0f} | - | - | - | {v['share_of_step']:.3f} |")
 out.append(f"\n## ncu --set full ({os.path.basename(rep)}, {points} points, one steady-state iteration, cold-cache serialised replays)\n")
 out.append(subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_profile_md.py"), rep], capture_output=True, text=True).stdout)
 if launches != "-" and os.path.exists(launches):

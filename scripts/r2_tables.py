@@ -29,6 +29,7 @@ for name in ("knn", "nvt_smooth", "nvt_classify", "flat_scalars", "update", "hal
         v = d["kernels"].get(name)
         cells.append("-" if not v else (f"{v['ms_per_step']:.3f} ({v['frac']:.3f})" if "frac" in v else f"{v['ms_per_step']:.3f}"))
     ab = one["kernels"].get(name, {}).get("algorithmic_bytes_per_point", "-")
+    ab = "-" if ab is None else ab
     print(f"| {name} | {ab} | " + " | ".join(cells) + " |")
 print(f"| whole iteration (B_iter = 294 B) | 294 | " + " | ".join(f"{d['ms_per_step']:.3f} ({d['roofline']['iteration_frac']:.3f} per GPU)" for d in lines) + " |")
 for d in lines:
