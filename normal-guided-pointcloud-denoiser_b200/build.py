@@ -10,7 +10,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libngpd.so")
+# NGPD_LIB_OUT / NGPD_EXTRA_NVCC_FLAGS: a second library with other macros next to the default one, for A/B runs (NGPD_LIBRARY selects it)
+LIB = os.environ.get("NGPD_LIB_OUT") or os.path.join(HERE, "libngpd.so")
 SOURCES = ["grid.cu", "knn.cu", "ball.cu", "nbr.cu", "mesh.cu", "orient.cu", "session.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--fmad=false", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--threads", "4"]
@@ -39,7 +40,7 @@ def build(force=False, verbose=False):
                 return LIB
             nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
             tmp = f"{LIB}.tmp.{os.getpid()}"
-            cmd = [nvcc] + NVCC_FLAGS + ["-shared", "-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
+            cmd = [nvcc] + NVCC_FLAGS + os.environ.get("NGPD_EXTRA_NVCC_FLAGS", "").split() + ["-shared", "-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
             res = subprocess.run(cmd, capture_output=True, text=True)

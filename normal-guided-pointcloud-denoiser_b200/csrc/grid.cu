@@ -359,9 +359,9 @@ static int build_once(ngpd_grid* G, const float* pos, int64_t n, double h, cudaS
     int64_t ntop = (int64_t)v.tbx * v.tby * v.tbz;
     NGPD_CUDA_OK(cudaMalloc(&G->top, ntop * sizeof(int)));
     NGPD_CUDA_OK(cudaMemsetAsync(G->top, 0xff, ntop * sizeof(int), stream));
-    // 4 padding entries: the streaming k-NN kernel loads candidates four at a time and masks the overrun
-    NGPD_CUDA_OK(cudaMalloc(&G->pts, ((size_t)n + 4) * sizeof(float4)));
-    NGPD_CUDA_OK(cudaMemsetAsync(G->pts + n, 0, 4 * sizeof(float4), stream));
+    // padding entries: the streaming k-NN kernels load up to KS_PAD candidates per step and mask the overrun
+    NGPD_CUDA_OK(cudaMalloc(&G->pts, ((size_t)n + KS_PAD) * sizeof(float4)));
+    NGPD_CUDA_OK(cudaMemsetAsync(G->pts + n, 0, KS_PAD * sizeof(float4), stream));
     uint64_t *keys = nullptr, *keys2 = nullptr;
     uint32_t *vals = nullptr, *vals2 = nullptr;
     int *flag = nullptr, *brick_start = nullptr;
@@ -451,7 +451,10 @@ extern "C" __attribute__((visibility("default"))) int ngpd_grid_create(const flo
     if (emax <= 0) emax = 1.0;
     // points per occupied cell: 0.4 k, but no more than for k = 32 -- longer rows of cells would not fit the streaming
     // search's 64-point range slots, and a k = 64 query is answered by the 5x5x5 tier anyway
-    const double target = std::max(2.0, 0.40 * (double)std::min(k_hint > 0 ? k_hint : 16, 32));
+#ifndef NGPD_GRID_KMAX
+#define NGPD_GRID_KMAX 32
+#endif
+    const double target = std::max(2.0, 0.40 * (double)std::min(k_hint > 0 ? k_hint : 16, NGPD_GRID_KMAX));
     double h;
     bool fixed = cell_size > 0.0f;
     if (fixed) {

@@ -11,6 +11,8 @@
 
 namespace ngpd {
 
+constexpr int KS_PAD = 8;   // padding entries behind GridView::pts: the streaming k-NN steps load up to KS_PAD candidates and mask the overrun
+
 struct GridView {
     const float4* pts;   // sorted points: x, y, z, original index (int bits)
     const int* top;      // [tbx*tby*tbz]

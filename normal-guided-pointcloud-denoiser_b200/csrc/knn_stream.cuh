@@ -37,7 +37,12 @@
 namespace ngpd {
 
 constexpr int KS_BATCH = 16;          // keys per lane between two selection rounds
-constexpr int KS_GROUP = 4;           // candidates per inner step (loads in flight); the point array is padded by KS_GROUP
+#ifndef NGPD_KS_GROUP_R1
+#define NGPD_KS_GROUP_R1 4
+#endif
+#ifndef NGPD_KS_GROUP_R2
+#define NGPD_KS_GROUP_R2 8
+#endif
 constexpr unsigned KS_NONE = 0xffffffffu;
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -65,6 +70,10 @@ struct KsCfg {
     static constexpr int IDBITS = SLOTBITS + OFFBITS;
     static constexpr unsigned IDMASK = (1u << IDBITS) - 1u;
     static constexpr int THREADS = R == 1 ? 128 : 64;
+    // candidates per inner step = independent loads in flight per lane.  The 5^3 tier runs one wave of blocks at 3 % occupancy: its
+    // duration is (steps per lane) x (latency of a divergent 16-byte gather), so eight loads per step instead of four nearly halve it.
+    static constexpr int GROUP = R == 1 ? NGPD_KS_GROUP_R1 : NGPD_KS_GROUP_R2;
+    static_assert(GROUP <= KS_PAD && 2 * GROUP <= KS_BATCH, "overrun past the padding / a step must fit the batch");
     static constexpr double UNIT = 1.0 / (double)(1 << (18 - (IDBITS - 9)));   // of the distance field, in h^2
 };
 
@@ -204,11 +213,11 @@ __device__ __forceinline__ bool knn_stream(KsTop<KT>& t, KsShared<R>& sm, const 
     unsigned* bp = b0;
     if (nr > 0) { int2 q = sm.rng[0][tid]; pp = g.pts + q.x; rem = q.y - q.x; r = 1; }
     while (__any_sync(FULL, rem > 0)) {
-        float4 p[KS_GROUP];
+        float4 p[C::GROUP];
 #pragma unroll
-        for (int u = 0; u < KS_GROUP; ++u) p[u] = __ldg(pp + u);       // may run past the range: the array is padded, `rem` masks
+        for (int u = 0; u < C::GROUP; ++u) p[u] = __ldg(pp + u);       // may run past the range: the array is padded, `rem` masks
 #pragma unroll
-        for (int u = 0; u < KS_GROUP; ++u) {
+        for (int u = 0; u < C::GROUP; ++u) {
             float dx = p[u].x - qx, dy = p[u].y - qy, dz = p[u].z - qz;
             float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
             bool valid = u < rem;
@@ -219,8 +228,8 @@ __device__ __forceinline__ bool knn_stream(KsTop<KT>& t, KsShared<R>& sm, const 
             bp += take ? C::THREADS : 0;
             rej = min(rej, take ? KS_NONE : key);
         }
-        rem -= KS_GROUP;
-        if (rem > 0) { pp += KS_GROUP; idv += KS_GROUP; }
+        rem -= C::GROUP;
+        if (rem > 0) { pp += C::GROUP; idv += C::GROUP; }
         else {
             if (C::PRUNE) {
                 // slots none of whose candidates could be taken: they count as dropped at their lower bound
@@ -229,7 +238,7 @@ __device__ __forceinline__ bool knn_stream(KsTop<KT>& t, KsShared<R>& sm, const 
             if (r < nr) { int2 q = sm.rng[r][tid]; pp = g.pts + q.x; rem = q.y - q.x; idv = (unsigned)r << C::OFFBITS; ++r; }
             else { pp = g.pts; rem = 0; }                               // done: keep the speculative loads in bounds
         }
-        if (__any_sync(FULL, bp > b0 + (KS_BATCH - KS_GROUP) * C::THREADS)) {
+        if (__any_sync(FULL, bp > b0 + (KS_BATCH - C::GROUP) * C::THREADS)) {
             ks_round<KT, R>(t, sm, (int)(bp - b0) / C::THREADS, rej);
             bp = b0;
             tau = min(bkey, t.key[KT - 1]);

@@ -233,8 +233,35 @@ __global__ void __launch_bounds__(128, K <= 16 ? 5 : 4) session_knn_rerank_kerne
             namespace ptx = cuda::ptx;
             __shared__ alignas(128) int rows_out[128 * K];
             int4* mine = reinterpret_cast<int4*>(rows_out + threadIdx.x * K);
+            constexpr int CH = K / 4;                                // 16-byte chunks per row
+            static_assert((CH & (CH - 1)) == 0 && CH <= 8, "the chunk rotation wants a power of two");
+#if defined(NGPD_ROWS_OUT_PLAIN)
 #pragma unroll
-            for (int c = 0; c < K / 4; ++c) mine[c] = make_int4(top.id[4 * c], top.id[4 * c + 1], top.id[4 * c + 2], top.id[4 * c + 3]);
+            for (int c = 0; c < CH; ++c) mine[c] = make_int4(top.id[4 * c], top.id[4 * c + 1], top.id[4 * c + 2], top.id[4 * c + 3]);
+#else
+            // A lane's row starts CH chunks after its neighbour's, so the lanes of a quarter warp that store chunk c of their rows hit
+            // 8 / CH bank groups CH times over (ncu round 2: 15 M of this kernel's 58 M shared-memory wavefronts were these conflicts).
+            // Lane L therefore stores its chunks in the order r, r+1, ... with r = (L / (8 / CH)) mod CH: in every step the eight
+            // lanes of a quarter warp cover the eight 16-byte bank groups.  The rotation of the row is log2(CH) rounds of selects.
+            int4 ch[CH];
+#pragma unroll
+            for (int c = 0; c < CH; ++c) ch[c] = make_int4(top.id[4 * c], top.id[4 * c + 1], top.id[4 * c + 2], top.id[4 * c + 3]);
+            const int rot = CH > 1 ? (((int)threadIdx.x & 31) / (CH > 1 ? 8 / CH : 1)) & (CH - 1) : 0;
+#pragma unroll
+            for (int bit = 1; bit < CH; bit <<= 1) {
+                const bool on = (rot & bit) != 0;
+                int4 t[CH];
+#pragma unroll
+                for (int c = 0; c < CH; ++c) {
+                    const int4 a = ch[c], b = ch[(c + bit) & (CH - 1)];
+                    t[c] = make_int4(on ? b.x : a.x, on ? b.y : a.y, on ? b.z : a.z, on ? b.w : a.w);
+                }
+#pragma unroll
+                for (int c = 0; c < CH; ++c) ch[c] = t[c];
+            }
+#pragma unroll
+            for (int c = 0; c < CH; ++c) mine[(c + rot) & (CH - 1)] = ch[c];          // ch[c] = chunk (c + rot) mod CH of the row
+#endif
             ptx::fence_proxy_async(ptx::space_shared);               // generic-proxy stores -> visible to the async proxy
             __syncwarp();
             if ((threadIdx.x & 31) == 0) {
