@@ -7,31 +7,17 @@ from pathlib import Path
 import numpy as np
 import torch
 
+from . import _io
+
 
 def _default_device():
     return "cuda" if torch.cuda.is_available() else "cpu"
 
 
 def read_obj(file_path: str):
-    """v [N,3] f64, vn [M,3] f64, face vertex ids [F,3] i64, face normal ids [Fn,3] i64 (0-based)."""
-    v, vn, fv, fn = [], [], [], []
-    with open(file_path, "r") as fh:
-        for line in fh:
-            if line.startswith("v "):
-                v.append(line.split()[1:4])
-            elif line.startswith("vn "):
-                vn.append(line.split()[1:4])
-            elif line.startswith("f "):
-                toks = line.split()[1:]
-                ids = [t.split("/") for t in toks]
-                # fan-triangulate polygons
-                for a in range(1, len(ids) - 1):
-                    tri = (ids[0], ids[a], ids[a + 1])
-                    fv.append([int(t[0]) - 1 for t in tri])
-                    if all(len(t) == 3 and t[2] != "" for t in tri):
-                        fn.append([int(t[2]) - 1 for t in tri])
-    arr = lambda x, dt: np.asarray(x, dtype=dt).reshape(-1, 3)
-    return arr(v, np.float64), arr(vn, np.float64), arr(fv, np.int64), arr(fn, np.int64)
+    """v [N,3] f64, vn [M,3] f64, face vertex ids [F,3] i64, face normal ids [Fn,3] i64 (0-based, polygons fan-triangulated).
+    Parsed by libngpd_io.so (threads over pieces of the mapped file); the reference goes through igl.read_obj (Object.py:80)."""
+    return _io.read_obj(file_path)
 
 
 def sample_points(pos: torch.Tensor, face: torch.Tensor, num: int):
@@ -104,8 +90,9 @@ def read_ply_vertices(file_path: str) -> np.ndarray:
             if not all(a in names for a in ("x", "y", "z")):
                 raise ValueError(f"{file_path}: vertex element without x, y, z")
             if fmt == "ascii":
-                rows = np.loadtxt(fh, dtype=np.float64, max_rows=count, ndmin=2) if count else np.zeros((0, len(names)))
-                return np.stack([rows[:, names.index(a)] for a in ("x", "y", "z")], axis=1).reshape(-1, 3)
+                cols = [names.index(a) for a in ("x", "y", "z")]
+                rows = _io.read_table(file_path, max(cols) + 1, offset=fh.tell(), rows=count) if count else np.zeros((0, max(cols) + 1))
+                return np.ascontiguousarray(rows[:, cols]).reshape(-1, 3)
             end = "<" if fmt == "binary_little_endian" else ">"
             rec = np.dtype([(n, end + t) for n, t in props])
             data = np.frombuffer(fh.read(count * rec.itemsize), dtype=rec, count=count)
@@ -135,13 +122,7 @@ class Pointcloud:
 
     def saveObj(self, file_path: str) -> None:
         """Object.py:58-69: `v x y z` lines then `vn` lines; refuses to overwrite (mode "x")."""
-        with open(file_path, "x") as f:
-            f.write("# File made by Ruben Band\n")
-            for row in self.v.detach().cpu().tolist():
-                f.write("v " + " ".join(str(x) for x in row) + "\n")
-            if self.n is not None:
-                for row in self.n.detach().cpu().tolist():
-                    f.write("vn " + " ".join(str(x) for x in row) + "\n")
+        _io.write_obj(file_path, self.v.detach().cpu().numpy(), None if self.n is None else self.n.detach().cpu().numpy(), exclusive=True)
         self.file_path = file_path
 
     @classmethod
@@ -205,7 +186,7 @@ class Pointcloud:
         assert path.is_file()
         assert path.suffix in (".xyz", ".clean_xyz")
         device = device if device is not None else _default_device()
-        pts = np.loadtxt(file_path, dtype=np.float64, usecols=(0, 1, 2)).reshape(-1, 3)
+        pts = _io.read_table(file_path, 3)
         pc = cls(torch.tensor(pts, dtype=torch.float, device=device))
         pc.file_path = file_path
         return pc

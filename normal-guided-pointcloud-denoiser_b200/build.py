@@ -24,7 +24,7 @@ def _newest(paths):
 def needs_build():
     if not os.path.exists(LIB):
         return True
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "ngpd.h")]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if os.path.isfile(os.path.join(CSRC, f))] + [os.path.join(HERE, "..", "include", "ngpd.h")]
     return _newest(deps) > os.path.getmtime(LIB)
 
 
@@ -56,5 +56,32 @@ def build(force=False, verbose=False):
             fcntl.flock(lock, fcntl.LOCK_UN)
 
 
+IO_LIB = os.path.join(HERE, "libngpd_io.so")
+IO_SOURCE = os.path.join(CSRC, "io", "ngpd_io.cpp")
+
+
+def build_io(force=False):
+    """libngpd_io.so: the host-side file readers / writer (include/ngpd_io.h), plain g++."""
+    import fcntl
+    with open(os.path.join(HERE, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            deps = [IO_SOURCE, os.path.join(HERE, "..", "include", "ngpd_io.h")]
+            if not force and os.path.exists(IO_LIB) and _newest(deps) <= os.path.getmtime(IO_LIB):
+                return IO_LIB
+            tmp = f"{IO_LIB}.tmp.{os.getpid()}"
+            cmd = [os.environ.get("CXX", "g++"), "-O3", "-std=c++17", "-shared", "-fPIC", "-fvisibility=hidden", "-pthread", "-o", tmp, IO_SOURCE]
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("g++ failed:\n" + res.stdout + res.stderr)
+            os.replace(tmp, IO_LIB)
+            return IO_LIB
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_io(force="--force" in sys.argv))
