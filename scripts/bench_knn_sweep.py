@@ -28,7 +28,9 @@ if world > 1:
 
 
 def timed(fn, reps=3):
-    fn(); torch.cuda.synchronize()
+    # two warm calls: the result tensor of call i is still alive while call i + 1 allocates its own, so the caching allocator needs
+    # two blocks before the timed region stops calling cudaMalloc (a 640 MB cudaMalloc costs 1-10 ms, more on some boxes)
+    fn(); fn(); torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
