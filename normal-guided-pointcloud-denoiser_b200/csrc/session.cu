@@ -197,8 +197,11 @@ __device__ __forceinline__ void session_write_row(int64_t s, int k, const int (&
 // (Measured and dropped: staging the window of 512-768 tree points around the block's rows in shared memory and gathering
 // the candidates' coordinates from there when they fall inside it -- 1.00 -> 1.17 ms at 10 M points, k = 16: the extra
 // select per candidate costs more than the L1 look-ups it saves.  6 instead of 5 blocks per SM (80 registers): no change.)
+#ifndef NGPD_RERANK_BLOCKS
+#define NGPD_RERANK_BLOCKS 5
+#endif
 template <int K, bool LEGACY_STORE>
-__global__ void __launch_bounds__(128, K <= 16 ? 5 : 4) session_knn_rerank_kernel(GridView g, const float4* __restrict__ pos, const uint8_t* __restrict__ owned,
+__global__ void __launch_bounds__(128, K <= 16 ? NGPD_RERANK_BLOCKS : 4) session_knn_rerank_kernel(GridView g, const float4* __restrict__ pos, const uint8_t* __restrict__ owned,
                                                                  int64_t n, int k, int32_t* __restrict__ idx, KnnTrack tr,
                                                                  int32_t* __restrict__ fail_list, int32_t* __restrict__ fail_count) {
     __shared__ KsCandTile<2 * K> tile;
@@ -776,6 +779,10 @@ __device__ __forceinline__ V3 clamp_to_original(V3 moved, V3 old, const float4* 
 }
 
 // one class: members move, everybody else is copied through to the other buffer (snapshot semantics)
+// MINB: resident blocks per SM.  The flat pass is latency-bound and wants every warp slot: at 100 M points 10 blocks per SM
+// (48 registers) take 2.98 ms, 12 (40 registers) 2.81 ms, 16 (32 registers; the 580 bytes of spills per thread sit on the other
+// strategies' paths) 2.54 ms.  feature_step / edge_step do more arithmetic per row and lose at 16 (0.68 / 0.85 against 0.56 / 0.62 ms
+// at 10 M points): they stay at 10 (profiles/r2_ab_measurements.md, section 7).
 template <int KU, int MINB>
 __global__ void __launch_bounds__(128, MINB) session_update_kernel(int kind, int key, Quad4 pos, Quad4 fn, const float4* __restrict__ edge,
                                                              const uint8_t* __restrict__ label, const uint8_t* __restrict__ owned,
@@ -1468,13 +1475,17 @@ extern "C" __attribute__((visibility("default"))) int ngpd_session_phase_update(
         S->sums_ready = false;
         return 0;
     }
-    // registers per thread: 10 blocks per SM (48 registers) keep more warps, 6 blocks (80 registers) let all 16 neighbour gathers of a
-    // row be in flight at once; NGPD_UPDATE_BLOCKS selects for A/B measurements (profiles/)
+    // registers per thread against resident warps: see session_update_kernel; NGPD_UPDATE_BLOCKS selects for A/B measurements (profiles/)
     static const char* ub_env = getenv("NGPD_UPDATE_BLOCKS");
-    static const int ub = ub_env ? atoi(ub_env) : 10;
+    static const int ub = ub_env ? atoi(ub_env) : 0;
 #define NGPD_UPDATE(KU_, MB_) session_update_kernel<KU_, MB_><<<(unsigned)cdiv(S->n, 128), 128, 0, st>>>(kind, key, Quad4{S->pos[S->cur]}, Quad4{S->fn}, S->edge, S->label, S->owned, \
                                                                             S->idx, S->n, S->idx_k, p->k_update, p->alpha[key], p->dmax, S->cd, orig, p->clamp_radius, S->pos[S->cur ^ 1])
-    if (fixed8) { if (ub == 6) NGPD_UPDATE(8, 6); else if (ub == 8) NGPD_UPDATE(8, 8); else NGPD_UPDATE(8, 10); }
+    if (fixed8) {
+        // default: 16 blocks per SM for flat_step, 10 for the others; NGPD_UPDATE_BLOCKS = 6 / 8 / 10 / 12 / 16 forces one (A/B runs)
+        const int blocks = ub ? ub : (kind == NGPD_STEP_FLAT ? 16 : 10);
+        if (blocks == 6) NGPD_UPDATE(8, 6); else if (blocks == 8) NGPD_UPDATE(8, 8); else if (blocks == 12) NGPD_UPDATE(8, 12);
+        else if (blocks == 16) NGPD_UPDATE(8, 16); else NGPD_UPDATE(8, 10);
+    }
     else NGPD_UPDATE(0, 10);
 #undef NGPD_UPDATE
     NGPD_CUDA_OK(cudaGetLastError());
