@@ -393,7 +393,12 @@ __device__ __forceinline__ void session_knn_body(KsShared<R>& sm, const GridView
 
 // rows = todo_list[0 .. *todo_count) when a list is given, every (owned) row otherwise
 template <int K, int KT>
-__global__ void __launch_bounds__(KsCfg<1>::THREADS, KT <= 16 ? 5 : (KT <= 32 ? 4 : 1))
+// resident blocks per SM of the search that keeps 2K = 32 candidates: 5 (96 registers, 76 bytes of spills) beats 4 (128 registers)
+// by 5 % and 3 (158, no spill) by 16 % on the first search of a session -- profiles/r2_ab_measurements.md, section 8
+#ifndef NGPD_FAST_BLOCKS_KT32
+#define NGPD_FAST_BLOCKS_KT32 5
+#endif
+__global__ void __launch_bounds__(KsCfg<1>::THREADS, KT <= 16 ? 5 : (KT <= 32 ? NGPD_FAST_BLOCKS_KT32 : 1))
 session_knn_fast_kernel(GridView g, const float4* __restrict__ pos, const uint8_t* __restrict__ owned, int64_t n, int k,
                         int32_t* __restrict__ idx, KnnTrack tr, const int32_t* __restrict__ todo_list,
                         const int32_t* __restrict__ todo_count, int32_t* __restrict__ fail_list, int32_t* __restrict__ fail_count,
