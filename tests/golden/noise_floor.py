@@ -3,7 +3,7 @@ fandisk input, and again with its input normals moved by 1 ulp.  Prints how far 
 ITSELF after Processor.denoise()'s two iterations (positions, normals, labels, Chamfer mean).  Run in the build container."""
 import os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "oracle")); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import ngpd_oracle as O
 from conftest import angle_between

@@ -4,7 +4,7 @@ LAPACK as the reference) run for three iterations on the recorded fandisk input,
 tests/test_gpu_parity.py::test_cpsd_loop_vs_reference is read against.  Run in the build container."""
 import os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "oracle")); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import ngpd_oracle as O
 from conftest import angle_between

@@ -435,7 +435,7 @@ def test_denoise_vs_reference_free_running(ng, fandisk):
     assert (ang > 1e-4).mean() < 0.0675
     cd = ng.TorchUtils.ChamferDistance(cu(fandisk["gt"]), p.graph.pos).double().mean().item()
     ref = fandisk["cd_final"].mean(dtype=np.float64)
-    # Chamfer yardstick (scripts/noise_floor.py, three 1-ulp trials): the reference differs from itself by 3.2e-4 .. 8.5e-4 relative
+    # Chamfer yardstick (tests/golden/noise_floor.py, three 1-ulp trials): the reference differs from itself by 3.2e-4 .. 8.5e-4 relative
     assert abs(cd - ref) / ref < 3e-3
 
 
@@ -483,7 +483,7 @@ def test_until_minimum_error_loop(ng, until_min):
     assert torch.equal(p.graph.pos, noisy)                                   # reset to the noisy input on exit
     scale = np.abs(until_min["pos0"]).max()
     err = np.abs(best.cpu().numpy() - until_min["pos_returned"]).max(axis=1) / scale
-    # yardstick (scripts/noise_floor.py): the reference's algorithm differs from ITSELF on 23.9 - 24.5 % of the positions
+    # yardstick (tests/golden/noise_floor.py): the reference's algorithm differs from ITSELF on 23.9 - 24.5 % of the positions
     # (> 1e-5, max 2.5e-3) after these three iterations when its input normals move by 1 ulp
     print(f"returned positions >1e-5 from the reference's: {(err > 1e-5).mean():.4%} (max {err.max():.2e})")
     assert (err > 1e-5).mean() < 0.239 and err.max() < 1e-2
@@ -881,7 +881,7 @@ def test_cpsd_loop_vs_reference(ng, cpsd):
         bad_n = (angle_between(f_n.cpu().numpy(), cpsd[t + "f_n"]) > 1e-4).mean()
         err = np.abs(g.pos.cpu().numpy() - cpsd[t + "pos_out"]).max(axis=1) / scale
         print(f"\nCPSD iteration {it}: labels agree {agree:.4%}, normals > 1e-4 rad {bad_n:.4%}, positions > 1e-5 {(err > 1e-5).mean():.4%}")
-        # Free-running: eigenvector signs feed the smoothing.  Yardstick (scripts/noise_floor_cpsd.py, three trials):
+        # Free-running: eigenvector signs feed the smoothing.  Yardstick (tests/golden/noise_floor_cpsd.py, three trials):
         # the reference's own algorithm, re-run with its input normals moved by 1 ulp, agrees with itself on
         #   labels      99.89-99.94 % / 99.74-99.77 % / 98.55-98.92 %   after iterations 1 / 2 / 3,
         #   normals     0.37-0.42 %  / 1.9-2.4 %     / 6.7-8.8 %       further than 1e-4 rad,
